@@ -1,0 +1,175 @@
+/* mmfm_b200.h -- C ABI of libmmfm_b200.so: the sm_100a kernels behind the forward/backward pass of the
+ * masked multi-modal encoder/decoder.
+ *
+ * The reference (yzhang511/multi_modal_foundation_model) has no FFI: its boundary for this path is the
+ * torch.nn.Module call `MultiModal.forward(mod_dict)` + `loss.backward()` (src/multi_modal/mm.py:242-308,
+ * src/trainer/base.py:103,194-195), and every arithmetic step under it is a PyTorch library call.  Each entry
+ * point below replaces one group of those library call sites (cited per function, paths relative to the
+ * reference root) and is what the Python host layer (multi_modal_foundation_model_b200/ops.py, ctypes) binds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; all buffers are owned by
+ *    the caller; the library allocates nothing on the device, never synchronises, and launches only on `stream`
+ *    (a cudaStream_t passed as void*).
+ *  - matrices are row-major; `ld*` are row pitches in ELEMENTS.  bf16 operands of the tensor-core kernels need
+ *    16-byte aligned base pointers and pitches that are multiples of 8 elements (TMA).
+ *  - return value 0 = launched; <0 = rejected (message via mmfm_last_error(), thread local).
+ */
+#ifndef MMFM_B200_H_
+#define MMFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMFM_ABI_VERSION 1
+
+const char* mmfm_last_error(void);
+int mmfm_abi_version(void);
+/* number of SMs of the current device (grid sizing); <=0 when no device */
+int mmfm_sm_count(void);
+
+/* Counter-based dropout stream shared by all kernels (restated in oracle/philox_ref.py).  Replaces the
+ * nn.Dropout / SDPA dropout_p draws of mm_utils.py:52,111,114 and encoder_embeddings.py:61. */
+typedef struct mmfm_dropout {
+  const unsigned long long* seed; /* device scalar (graph-replay safe); NULL = dropout off */
+  uint32_t site;                  /* stream id of the dropout site */
+  uint32_t thresh;                /* element dropped iff random byte < thresh; 0 = off */
+  float scale;                    /* 256 / (256 - thresh) */
+} mmfm_dropout;
+
+/* ---- tensor-core GEMM (tcgen05 / TMEM / TMA) ------------------------------------------------------------ */
+enum mmfm_act {
+  MMFM_ACT_NONE = 0,
+  MMFM_ACT_GELU = 1,      /* D <- gelu_erf(v); D2 (optional) <- v   (mm_utils.py:51) */
+  MMFM_ACT_SOFTSIGN = 2,  /* D <- softsign(v) * act_scale           (encoder_embeddings.py:52) */
+  MMFM_ACT_DGELU = 3,     /* D <- v * gelu'(aux)                    (backward of mm_utils.py:51) */
+  MMFM_ACT_DSOFTSIGN = 4  /* D <- v * act_scale * (1-|aux/act_scale|)^2   (backward of encoder_embeddings.py:52) */
+};
+
+typedef struct mmfm_gemm_args {
+  const void* A; long long lda;  /* bf16 [M,K] */
+  const void* B; long long ldb;  /* bf16 [N,K]  (an nn.Linear weight, or its transpose for dgrad) */
+  int M, N, K;
+  void* D; long long ldd;        /* [M_out, N] bf16 or fp32 */
+  int d_fp32;
+  void* D2;                      /* optional bf16 second output, pitch ldd */
+  const float* bias;             /* [N] or NULL */
+  const float* res; long long ldr; /* optional fp32 [M_out, >=N], added last, indexed by the OUTPUT row */
+  const void* aux; long long ldaux; /* bf16 [M, >=N] for DGELU / DSOFTSIGN */
+  int act; float act_scale;
+  mmfm_dropout drop;             /* over the (M,N) field, applied after the activation */
+  /* output row remap of the token-embedding GEMM (writes modality m's tokens straight into the packed
+   * (B, S=M*T, H) layout, replacing torch.cat of mm.py:98-108):  out_row = (r / remap_T) * remap_S + remap_off +
+   * r % remap_T ; remap_T == 0 = identity */
+  int remap_T, remap_S, remap_off;
+  /* optional [S] flags: token position p = remap_off + r % remap_T (or r % remap_S when remap_T == 0) is zeroed
+   * before `res` is added (mm.py:147-149,169-171) */
+  const unsigned char* row_zero;
+} mmfm_gemm_args;
+
+/* D = epilogue(A . B^T).  Replaces nn.Linear forward (mm_utils.py:51-52,107-109,114,145-147,152;
+ * encoder_embeddings.py:50,54; decoder_embeddings.py:50,54,107; mm.py:292) and its autograd dgrad. */
+int mmfm_gemm_tn(const mmfm_gemm_args* args, void* stream);
+
+/* dW[NO,KI] += dY[R,NO]^T . X[R,KI]  (fp32 accumulate with red.global.add; caller zeroes dW once per step).
+ * Replaces the autograd wgrad of every nn.Linear on the path. */
+int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI, float* dW,
+                    long long ldw, void* stream);
+/* out[c] += sum_r dY[r,c]  (bias gradient) */
+int mmfm_colsum_bf16(const void* dY, long long ld, int R, int NO, float* out, void* stream);
+
+/* ---- conversions ------------------------------------------------------------------------------------- */
+/* fp32 [R,C] (pitch ldx) -> bf16 [R,C] (pitch ldy); optional transposed copy yt [C,R] (pitch ldyt) */
+int mmfm_cast_bf16(const float* x, long long ldx, void* y, long long ldy, void* yt, long long ldyt, int R, int C,
+                   void* stream);
+
+/* ---- LayerNorm (nn.LayerNorm(H), eps 1e-5: encoder_embeddings.py:98-100, decoder_embeddings.py:116-126,
+ *      mm.py:72,77) -------------------------------------------------------------------------------------- */
+/* y(bf16) = LN(x) ; mean/rstd saved.  modmajor_T > 0: row (b,s) of x is written to row (s/T)*(B*T) + b*T + s%T
+ * (modality-major layout feeding the per-modality heads, decoder_embeddings.py:105-107), B = R/S. */
+int mmfm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       int R, int H, float eps, int modmajor_T, int S, void* stream);
+/* dx = dres + LN'(dy) ; optional bf16 copy dxb = bf16(dropout(dx)) ; dgamma/dbeta += column sums.
+ * dy is read through the same modality-major remap when modmajor_T > 0. */
+int mmfm_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* dres, float* dx, void* dxb, const mmfm_dropout* drop, float* dgamma,
+                       float* dbeta, int R, int H, int modmajor_T, int S, void* stream);
+
+/* ---- masked attention (flash-style; F.scaled_dot_product_attention with the (B,S,S) bool masks of
+ *      mm.py:152-158,178-194 evaluated as predicates; mm_utils.py:105-112,143-150) ------------------------ */
+enum mmfm_mask_mode {
+  MMFM_MASK_KEY = 0,       /* allowed(i,j) = key_valid[b,j]                      (decoder self, default) */
+  MMFM_MASK_KEY_OR_DIAG = 1, /* key_valid[b,j] | (i == j)                       (encoder self + cross) */
+  MMFM_MASK_CAUSAL = 2     /* j <= i  (key padding dropped, mm.py:183-185) */
+};
+typedef struct mmfm_attn_args {
+  const void* q; long long ldq;   /* bf16 rows (b*Sq + i), head h at columns [h*d, (h+1)*d) */
+  const void* k; long long ldk;   /* bf16 rows (b*Sk + j) */
+  const void* v; long long ldv;
+  void* o; long long ldo;         /* bf16 [B*Sq, h*d], after the output dropout (mm_utils.py:114) */
+  float* lse;                     /* [B, h, Sq] log-sum-exp of the scaled masked scores */
+  const unsigned char* key_valid; /* [B, Sk] */
+  const short* mod_q; const short* mod_k; /* optional [Sq],[Sk] modality ids: allowed |= mod_q[i] != mod_k[j] (sep) */
+  int B, n_heads, Sq, Sk, d_head;
+  int mask_mode;
+  float scale;                    /* 1/sqrt(d_head) */
+  mmfm_dropout drop_p;            /* on the probabilities: rows (b*h+hh)*Sq+i, cols Sk */
+  mmfm_dropout drop_o;            /* on the output: rows b*Sq+i, cols h*d */
+  /* backward only */
+  const void* d_o; long long lddo; /* bf16 gradient wrt the (pre output-dropout) attention output */
+  void* dq; long long lddq;
+  void* dk; long long lddk;
+  void* dv; long long lddv;
+} mmfm_attn_args;
+int mmfm_attention_fwd(const mmfm_attn_args* args, void* stream);
+int mmfm_attention_bwd(const mmfm_attn_args* args, void* stream);
+
+/* ---- token embedding glue ---------------------------------------------------------------------------- */
+/* masks: zero_flags[s] = (mask[0,s] == 1) (mm.py:147,169 -- sample 0's mask zeroes the whole batch);
+ * key_valid[b,s] = attn[b,s] != 0; n_examples[m] = channels[m] * sum(mask[:, m*T:(m+1)*T]) (mm.py:231);
+ * inv_n[0] = 1 / sum_m n_examples[m] (mm.py:237). */
+int mmfm_mask_prep(const long long* mask, const long long* attn, int B, int S, int T, const int* channels_host,
+                   int n_mod, unsigned char* zero_flags, unsigned char* key_valid, long long* n_examples,
+                   float* inv_n, void* stream);
+/* emb[b, off+t, :] = mod_emb[:] + pos_embed[ts[b,t], :]  (encoder_embeddings.py:56-59) */
+int mmfm_embed_assemble(const float* mod_emb_row, const float* pos_embed, const long long* ts, float* emb, int B,
+                        int T, int S, int off, int H, void* stream);
+/* gradient of the above: dpos[ts[b,t], :] += g[b, off+t, :] (+ g2) ; dmod[:] += sum_{b,t} */
+int mmfm_embed_assemble_bwd(const float* g, const float* g2, const long long* ts, float* dpos, float* dmod, int B,
+                            int T, int S, int off, int H, void* stream);
+/* d_tok (bf16 [B*T, H]) = dropout_mask( row_zero ? 0 : dx[b, off+t, :] )  -- backward of the embedding epilogue */
+int mmfm_embed_grad_prep(const float* dx, void* dtok, const unsigned char* row_zero, const mmfm_dropout* drop, int B,
+                         int T, int S, int off, int H, void* stream);
+/* small-channel modality (C <= 8, e.g. behaviour C=2): the whole embedder / head as SIMT kernels
+ * (encoder_embeddings.py:50-61; decoder_embeddings.py:105-107) */
+int mmfm_smallc_embed_fwd(const float* in, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const float* emb, float* x, float* hid, const unsigned char* row_zero,
+                          const mmfm_dropout* drop, float act_scale, int act, int B, int T, int S, int off, int C,
+                          int H, void* stream);
+int mmfm_smallc_embed_bwd(const float* in, const float* hid, const float* W2, const float* dx,
+                          const unsigned char* row_zero, const mmfm_dropout* drop, float act_scale, int act,
+                          float* dW1, float* db1, float* dW2, float* db2, int B, int T, int S, int off, int C, int H,
+                          void* stream);
+int mmfm_smallc_head_fwd(const void* y, const float* W, const float* b, float* preds, int R, int H, int C,
+                         void* stream);
+int mmfm_smallc_head_bwd(const void* y, const float* W, const void* dpreds, long long lddp, void* dy, float* dW,
+                         float* db, int R, int H, int C, void* stream);
+
+/* ---- fused masked loss + gradient (mm.py:217-239; nn.PoissonNLLLoss(log_input=True) :80, nn.MSELoss :81) -- */
+enum mmfm_loss_kind { MMFM_LOSS_POISSON = 0, MMFM_LOSS_MSE = 1 };
+/* loss_sum[0] += sum(mask * ell(preds, targets)) ; dpreds(bf16, pitch lddp) = mask * ell' * inv_n[0] */
+int mmfm_loss_fwd_bwd(const float* preds, const float* targets, const long long* mask, long long mask_ld,
+                      const float* inv_n, int kind, int B, int T, int C, float* partials, int n_partials,
+                      void* dpreds, long long lddp, void* stream);
+/* mod_loss[m] = fixed-order sum of partials[m*n_partials ...]; loss = sum_m mod_loss / sum_m n_examples */
+int mmfm_loss_finalize(const float* partials, int n_partials, int n_mod, const long long* n_examples, float* mod_loss,
+                       float* loss, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMFM_B200_H_ */

@@ -1,0 +1,72 @@
+#include "host_util.h"
+
+#include <stdarg.h>
+
+#include <mutex>
+
+namespace mmfm {
+
+static thread_local char g_err[1024] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // The driver entry point is resolved at run time so the library links without libcuda (no GPU at build).
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  MMFM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  MMFM_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base %p not 16-byte aligned", base);
+  MMFM_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch %llu elements is not a multiple of 16 bytes",
+               (unsigned long long)ld);
+  MMFM_REQUIRE(box_rows <= 256 && box_cols <= 256, "TMA box too large");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle s = swz == TMA_SW_128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                         : swz == TMA_SW_64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                         : swz == TMA_SW_32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                            : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMFM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+  return 0;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace mmfm

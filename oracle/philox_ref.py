@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of the dropout random stream of the CUDA path.
+
+The reference draws dropout masks from PyTorch's generator (``nn.Dropout`` /
+``F.scaled_dot_product_attention(dropout_p=...)``, reference ``src/multi_modal/mm_utils.py:52,111,114``),
+whose Philox offsets a foreign kernel cannot reproduce.  The CUDA path therefore defines its OWN
+counter-based stream (``csrc/philox.cuh``) and this file restates it bit for bit so that training-mode
+activations/gradients can be checked against the oracle with identical masks:
+
+* generator: Philox4x32 with ``PHILOX_ROUNDS`` rounds, key = the 64-bit step seed,
+  counter = (group_lo, group_hi, site, 0);
+* one call yields 16 bytes = 16 consecutive elements of one row:
+  group = row * ceil(cols/16) + col // 16, byte index = col % 16 (little-endian inside each word);
+* element is DROPPED iff byte < round(p * 256); kept elements are scaled by 256 / (256 - round(p*256)).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PHILOX_ROUNDS = 7
+_M0 = np.uint64(0xD2511F53)
+_M1 = np.uint64(0xCD9E8D57)
+_W0 = 0x9E3779B9
+_W1 = 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def drop_threshold(p: float) -> int:
+    """Byte threshold: an element is dropped iff its random byte < threshold."""
+    t = int(round(float(p) * 256.0))
+    return max(0, min(255, t))
+
+
+def keep_scale(p: float) -> float:
+    t = drop_threshold(p)
+    return 256.0 / (256.0 - t)
+
+
+def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = PHILOX_ROUNDS):
+    """Vectorised Philox4x32; counters are uint32 arrays, key two python ints."""
+    c0 = c0.astype(np.uint64)
+    c1 = c1.astype(np.uint64)
+    c2 = c2.astype(np.uint64)
+    c3 = c3.astype(np.uint64)
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(rounds):
+        p0 = _M0 * c0
+        p1 = _M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + _W0) & 0xFFFFFFFF
+        k1 = (k1 + _W1) & 0xFFFFFFFF
+    return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def random_bytes(seed: int, site: int, rows: int, cols: int) -> np.ndarray:
+    """The (rows, cols) uint8 random field of one dropout site."""
+    gpr = (cols + 15) // 16
+    g = np.arange(rows * gpr, dtype=np.uint64)
+    c0 = (g & _MASK32).astype(np.uint32)
+    c1 = (g >> np.uint64(32)).astype(np.uint32)
+    c2 = np.full_like(c0, np.uint32(site & 0xFFFFFFFF))
+    c3 = np.zeros_like(c0)
+    w = philox4x32(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=1)  # (G, 4) uint32, little endian bytes
+    by = words.view(np.uint8).reshape(rows, gpr * 16)
+    return by[:, :cols]
+
+
+def keep_mask(seed: int, site: int, rows: int, cols: int, p: float) -> np.ndarray:
+    """float32 (rows, cols): 0 where dropped, keep_scale(p) where kept."""
+    if p <= 0.0:
+        return np.ones((rows, cols), dtype=np.float32)
+    by = random_bytes(seed, site, rows, cols)
+    return (by >= drop_threshold(p)).astype(np.float32) * np.float32(keep_scale(p))
+
+
+# Dropout site identifiers (must match csrc/philox.cuh).  site = kind + 16 * layer + 4096 * side
+SITE_EMBED = 0        # + modality index in the layer slot
+SITE_ATTN_PROB = 1
+SITE_ATTN_OUT = 2
+SITE_XATTN_PROB = 3
+SITE_XATTN_OUT = 4
+SITE_MLP = 5
+SIDE_ENC = 0
+SIDE_DEC = 1
+
+
+def site_id(kind: int, layer: int, side: int) -> int:
+    return kind + 16 * layer + 4096 * side
