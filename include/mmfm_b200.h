@@ -119,8 +119,12 @@ typedef struct mmfm_attn_args {
   float scale;                    /* 1/sqrt(d_head) */
   mmfm_dropout drop_p;            /* on the probabilities: rows (b*h+hh)*Sq+i, cols Sk */
   mmfm_dropout drop_o;            /* on the output: rows b*Sq+i, cols h*d */
+  unsigned short* p_keep;         /* [B, h, Sq, ceil(Sk/64), 4] keep bits of the probability dropout (written by
+                                     fwd, read by bwd); may be NULL when drop_p is off */
   /* backward only */
-  const void* d_o; long long lddo; /* bf16 gradient wrt the (pre output-dropout) attention output */
+  void* d_o; long long lddo;      /* bf16 [B*Sq, h*d]: in = gradient wrt `o`; overwritten with the gradient wrt the
+                                     attention output before the output dropout */
+  float* delta;                   /* scratch [B, h, Sq]: rowsum(dO * O) */
   void* dq; long long lddq;
   void* dk; long long lddk;
   void* dv; long long lddv;
@@ -129,16 +133,27 @@ int mmfm_attention_fwd(const mmfm_attn_args* args, void* stream);
 int mmfm_attention_bwd(const mmfm_attn_args* args, void* stream);
 
 /* ---- token embedding glue ---------------------------------------------------------------------------- */
-/* masks: zero_flags[s] = (mask[0,s] == 1) (mm.py:147,169 -- sample 0's mask zeroes the whole batch);
- * key_valid[b,s] = attn[b,s] != 0; n_examples[m] = channels[m] * sum(mask[:, m*T:(m+1)*T]) (mm.py:231);
- * inv_n[0] = 1 / sum_m n_examples[m] (mm.py:237). */
-int mmfm_mask_prep(const long long* mask, const long long* attn, int B, int S, int T, const int* channels_host,
-                   int n_mod, unsigned char* zero_flags, unsigned char* key_valid, long long* n_examples,
-                   float* inv_n, void* stream);
-/* emb[b, off+t, :] = mod_emb[:] + pos_embed[ts[b,t], :]  (encoder_embeddings.py:56-59) */
+#define MMFM_MAX_MOD 8
+/* Per-modality (B,T) int64 masks as strided views (element strides), so `eval_mask[:, :, 0]` of a (B,T,C) tensor
+ * (mm.py:269-270) is passed without a copy.  mask[m] == NULL means "nothing masked". */
+typedef struct mmfm_mask_args {
+  int n_mod, B, T;
+  const long long* mask[MMFM_MAX_MOD]; long long mask_sb[MMFM_MAX_MOD]; long long mask_st[MMFM_MAX_MOD];
+  const long long* attn[MMFM_MAX_MOD]; long long attn_sb[MMFM_MAX_MOD]; long long attn_st[MMFM_MAX_MOD];
+  int channels[MMFM_MAX_MOD];
+} mmfm_mask_args;
+/* With S = n_mod*T and mk = mask & attn (mm.py:270):
+ *   zero_flags[s]   = (mk[0,s] == 1)      (mm.py:147,169 -- sample 0's mask zeroes the whole batch)
+ *   key_valid[b,s]  = attn[b,s] != 0      (mm.py:152-158,178-194)
+ *   tok_mask[b,s]   = mk[b,s] != 0        (loss weights, mm.py:229)
+ *   n_examples[m]   = channels[m] * sum(mk[:, m*T:(m+1)*T])   (mm.py:231)
+ *   inv_n[0]        = 1 / sum_m n_examples[m]                  (mm.py:237) */
+int mmfm_mask_prep(const mmfm_mask_args* args, unsigned char* zero_flags, unsigned char* key_valid,
+                   unsigned char* tok_mask, long long* n_examples, float* inv_n, void* stream);
+/* emb[b, off+t, :] = mod_emb_row[:] + pos_embed[ts[b,t], :]  (encoder_embeddings.py:56-59); pos_embed may be NULL */
 int mmfm_embed_assemble(const float* mod_emb_row, const float* pos_embed, const long long* ts, float* emb, int B,
                         int T, int S, int off, int H, void* stream);
-/* gradient of the above: dpos[ts[b,t], :] += g[b, off+t, :] (+ g2) ; dmod[:] += sum_{b,t} */
+/* gradient of the above: dpos[ts[b,t], :] += g[b, off+t, :] (+ g2) ; dmod[:] += sum_{b,t} (same) */
 int mmfm_embed_assemble_bwd(const float* g, const float* g2, const long long* ts, float* dpos, float* dmod, int B,
                             int T, int S, int off, int H, void* stream);
 /* d_tok (bf16 [B*T, H]) = dropout_mask( row_zero ? 0 : dx[b, off+t, :] )  -- backward of the embedding epilogue */
@@ -161,13 +176,29 @@ int mmfm_smallc_head_bwd(const void* y, const float* W, const void* dpreds, long
 
 /* ---- fused masked loss + gradient (mm.py:217-239; nn.PoissonNLLLoss(log_input=True) :80, nn.MSELoss :81) -- */
 enum mmfm_loss_kind { MMFM_LOSS_POISSON = 0, MMFM_LOSS_MSE = 1 };
-/* loss_sum[0] += sum(mask * ell(preds, targets)) ; dpreds(bf16, pitch lddp) = mask * ell' * inv_n[0] */
-int mmfm_loss_fwd_bwd(const float* preds, const float* targets, const long long* mask, long long mask_ld,
-                      const float* inv_n, int kind, int B, int T, int C, float* partials, int n_partials,
-                      void* dpreds, long long lddp, void* stream);
-/* mod_loss[m] = fixed-order sum of partials[m*n_partials ...]; loss = sum_m mod_loss / sum_m n_examples */
-int mmfm_loss_finalize(const float* partials, int n_partials, int n_mod, const long long* n_examples, float* mod_loss,
+/* preds, targets fp32 [B*T, C] contiguous; tok_mask [B,S] bytes, this modality at columns off..off+T-1.
+ * partials[i] = CTA i's share of sum(mask * ell(preds, targets)) (n_partials CTAs, fixed-order finalize);
+ * dpreds (bf16, pitch lddp) = mask * ell' * inv_n[0]. */
+int mmfm_loss_fwd_bwd(const float* preds, const float* targets, const unsigned char* tok_mask, int S, int off,
+                      const float* inv_n, int kind, int B, int T, int C, float* partials, int n_partials, void* dpreds,
+                      long long lddp, void* stream);
+/* mod_loss[m] = sum of partials[m*n_partials ...]; loss = sum_m mod_loss[m] * inv_n[0] */
+int mmfm_loss_finalize(const float* partials, int n_partials, int n_mod, const float* inv_n, float* mod_loss,
                        float* loss, void* stream);
+
+/* ---- multi-tensor cast: bf16 shadows (and transposed shadows for dgrad) of all fp32 weights in one launch -- */
+typedef struct mmfm_cast_item {
+  const float* src; long long ld_src;   /* fp32 [rows, cols] */
+  void* dst; long long ld_dst;          /* bf16 [rows, cols] or NULL */
+  void* dst_t; long long ld_dst_t;      /* bf16 [cols, rows] or NULL */
+  int rows, cols;
+  int tile_start;                       /* exclusive prefix sum of ceil(rows/32)*ceil(cols/32) over the items */
+  int pad_;
+} mmfm_cast_item;
+int mmfm_cast_bf16_multi(const mmfm_cast_item* items_dev, int n_items, int total_tiles, void* stream);
+/* x[0..n) *= scale_dev[0]; returns at once on the device when the scale is exactly 1 (upstream gradient of the
+ * scalar loss, trainer/base.py:195 always passes 1) */
+int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
 
 #ifdef __cplusplus
 }

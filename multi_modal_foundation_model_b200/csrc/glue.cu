@@ -1,0 +1,683 @@
+// Bandwidth kernels around the GEMM / attention core: mask preparation, embedding assembly and its gradient,
+// the small-channel (C <= 8) embedder / head, the fused masked loss + gradient, multi-tensor fp32 -> bf16 casts.
+//
+// Reference call sites replaced (paths relative to the reference root):
+//   mask_prep            mm.py:266-275 (mask[:,:,0] & attn), :147,169 (argwhere(mask[0]==1)), :231,237 (counts)
+//   embed_assemble(+bwd) encoder_embeddings.py:56-59 / decoder_embeddings.py:56-59 (mod_emb + pos_embed gather)
+//   embed_grad_prep      autograd of the in-place token zeroing (mm.py:149,171) and embedding dropout (:61)
+//   smallc_*             encoder_embeddings.py:50-61 and decoder_embeddings.py:105-107 for C <= 8 (behaviour, C = 2)
+//   loss_fwd_bwd         mm.py:217-239 with nn.PoissonNLLLoss(log_input=True) (:80) and nn.MSELoss (:81)
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/mmfm_b200.h"
+
+namespace mmfm {
+
+MMFM_DEVINL float block_sum(float v, float* sh) {  // sh: >= 32 floats
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (warp == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  return sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mask preparation (single CTA; B*S elements)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) mask_prep_kernel(const mmfm_mask_args a, unsigned char* __restrict__ zero_flags,
+                                                          unsigned char* __restrict__ key_valid,
+                                                          unsigned char* __restrict__ tok_mask,
+                                                          long long* __restrict__ n_examples,
+                                                          float* __restrict__ inv_n) {
+  __shared__ float sh[32];
+  __shared__ long long total;
+  const int S = a.n_mod * a.T;
+  if (threadIdx.x == 0) total = 0;
+  for (int m = 0; m < a.n_mod; ++m) {
+    int cnt = 0;
+    for (int e = threadIdx.x; e < a.B * a.T; e += blockDim.x) {
+      const int b = e / a.T, t = e - b * a.T;
+      const long long at = a.attn[m][(long long)b * a.attn_sb[m] + (long long)t * a.attn_st[m]];
+      long long mk = a.mask[m] ? a.mask[m][(long long)b * a.mask_sb[m] + (long long)t * a.mask_st[m]] : 0;
+      mk &= at;  // mm.py:270
+      const long long o = (long long)b * S + m * a.T + t;
+      key_valid[o] = at != 0;
+      tok_mask[o] = (unsigned char)(mk != 0);
+      if (b == 0) zero_flags[m * a.T + t] = (mk == 1);
+      cnt += (int)mk;  // mask entries are 0/1 (mm.py:231 sums the expanded mask)
+    }
+    const float c = block_sum((float)cnt, sh);  // exact: counts < 2^24
+    if (threadIdx.x == 0) {
+      const long long n = (long long)(c + 0.5f) * a.channels[m];
+      n_examples[m] = n;
+      total += n;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) inv_n[0] = 1.0f / (float)total;  // total == 0 -> inf (reference: NaN loss)
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// embedding assembly
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __restrict__ mod_row,
+                                                              const float* __restrict__ pos,
+                                                              const long long* __restrict__ ts, float* __restrict__ emb,
+                                                              int B, int T, int S, int off, int H) {
+  const int hv = H >> 2;
+  const long long total = (long long)B * T * hv;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / hv;
+    const int c = (int)(e - r * hv);
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    float4 v = __ldg(reinterpret_cast<const float4*>(mod_row) + c);
+    if (pos) {
+      const float4 pv = __ldg(reinterpret_cast<const float4*>(pos + ts[r] * H) + c);
+      v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+    }
+    reinterpret_cast<float4*>(emb + (b * S + off + t) * H)[c] = v;
+  }
+}
+
+// grid (T, B-chunks); block H/4 threads (one float4 column group each).  Consecutive samples that hit the same
+// position row are summed in registers before one red.global per column.
+__global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const float* __restrict__ g2,
+                                          const long long* __restrict__ ts, float* __restrict__ dpos,
+                                          float* __restrict__ dmod, int B, int T, int S, int off, int H, int bchunk) {
+  const int t = blockIdx.x;
+  const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  for (int c = threadIdx.x; c < (H >> 2); c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = acc;
+    long long cur = -1;
+    for (int b = b0; b < b1; ++b) {
+      const long long row = ((long long)b * S + off + t) * H;
+      float4 v = __ldg(reinterpret_cast<const float4*>(g + row) + c);
+      if (g2) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(g2 + row) + c);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      accm.x += v.x; accm.y += v.y; accm.z += v.z; accm.w += v.w;
+      if (dpos) {
+        const long long idx = ts[(long long)b * T + t];
+        if (idx != cur) {
+          if (cur >= 0) {
+            float* d = dpos + cur * H + c * 4;
+            atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+          }
+          cur = idx;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (dpos && cur >= 0) {
+      float* d = dpos + cur * H + c * 4;
+      atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    }
+    float* dm = dmod + c * 4;
+    atomicAdd(dm, accm.x); atomicAdd(dm + 1, accm.y); atomicAdd(dm + 2, accm.z); atomicAdd(dm + 3, accm.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) embed_grad_prep_kernel(const float* __restrict__ dx, bf16* __restrict__ dtok,
+                                                               const unsigned char* __restrict__ row_zero, DropCfg drop,
+                                                               int B, int T, int S, int off, int H) {
+  const int hv = H >> 2;
+  const long long total = (long long)B * T * hv;
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  const uint32_t gpr = (uint32_t)((H + 15) >> 4);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / hv;
+    const int c = (int)(e - r * hv) * 4;
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(row_zero && row_zero[off + t])) {
+      v = __ldg(reinterpret_cast<const float4*>(dx + (b * S + off + t) * H + c));
+      if (drop.thresh != 0u) {
+        const uint4 w = drop_bytes16(seed, drop.site, (uint64_t)r, gpr, (uint32_t)(c >> 4));
+        const int b0 = c & 15;
+        v.x = drop_byte(w, b0) < drop.thresh ? 0.f : v.x * drop.scale;
+        v.y = drop_byte(w, b0 + 1) < drop.thresh ? 0.f : v.y * drop.scale;
+        v.z = drop_byte(w, b0 + 2) < drop.thresh ? 0.f : v.z * drop.scale;
+        v.w = drop_byte(w, b0 + 3) < drop.thresh ? 0.f : v.w * drop.scale;
+      }
+    }
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dtok + r * H + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small-channel embedder (C <= 8 -> hidden 2C <= 16): SIMT
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxC = 8;
+constexpr int kMaxC2 = 16;
+
+MMFM_DEVINL float act_fwd(float v, int act, float scale) {
+  if (act == MMFM_ACT_SOFTSIGN) v = softsign(v);
+  return v * scale;
+}
+
+// one CTA per token row; threads stride over H
+__global__ void __launch_bounds__(256) smallc_embed_fwd_kernel(const float* __restrict__ in, const float* __restrict__ W1,
+                                                                const float* __restrict__ b1, const float* __restrict__ W2,
+                                                                const float* __restrict__ b2, const float* __restrict__ emb,
+                                                                float* __restrict__ x, float* __restrict__ hid,
+                                                                const unsigned char* __restrict__ row_zero, DropCfg drop,
+                                                                float act_scale, int act, int B, int T, int S, int off,
+                                                                int C, int H) {
+  __shared__ float sh[kMaxC2];
+  const long long r = blockIdx.x;
+  const long long b = r / T;
+  const int t = (int)(r - b * T);
+  const int C2 = 2 * C;
+  if (threadIdx.x < C2) {
+    float a = b1 ? b1[threadIdx.x] : 0.f;
+    for (int c = 0; c < C; ++c) a += in[r * C + c] * W1[threadIdx.x * C + c];
+    a = act_fwd(a, act, act_scale);
+    sh[threadIdx.x] = a;
+    hid[r * C2 + threadIdx.x] = a;
+  }
+  __syncthreads();
+  const bool zero = row_zero && row_zero[off + t];
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  const uint32_t gpr = (uint32_t)((H + 15) >> 4);
+  const long long orow = (b * S + off + t) * H;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float v = b2 ? b2[h] : 0.f;
+    for (int j = 0; j < C2; ++j) v += sh[j] * W2[h * C2 + j];
+    if (drop.thresh != 0u)
+      v = drop_byte_at(seed, drop.site, (uint64_t)r, gpr, (uint32_t)h) < drop.thresh ? 0.f : v * drop.scale;
+    if (zero) v = 0.f;
+    x[orow + h] = v + emb[orow + h];
+  }
+}
+
+// CTA = chunk of rows, thread = hidden column h (blockDim == H <= 1024).  Register partials for dW2/db2 (thread h)
+// and dW1/db1 (threads j < 2C); flushed with atomics at the end.
+__global__ void smallc_embed_bwd_kernel(const float* __restrict__ in, const float* __restrict__ hid,
+                                        const float* __restrict__ W2, const float* __restrict__ dx,
+                                        const unsigned char* __restrict__ row_zero, DropCfg drop, float act_scale, int act,
+                                        float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                        float* __restrict__ db2, int B, int T, int S, int off, int C, int H,
+                                        int rows_per_cta) {
+  __shared__ float red[32][kMaxC2 + 1];
+  const int h = threadIdx.x, warp = h >> 5, lane = h & 31, nw = blockDim.x >> 5;
+  const int C2 = 2 * C;
+  const long long R = (long long)B * T;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  const uint32_t gpr = (uint32_t)((H + 15) >> 4);
+  float w2[kMaxC2], aw2[kMaxC2], aw1[kMaxC];
+  float ab2 = 0.f, ab1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxC2; ++j) {
+    w2[j] = (j < C2) ? W2[h * C2 + j] : 0.f;
+    aw2[j] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) aw1[c] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    float d = 0.f;
+    if (!(row_zero && row_zero[off + t])) {
+      d = dx[(b * S + off + t) * H + h];
+      if (drop.thresh != 0u)
+        d = drop_byte_at(seed, drop.site, (uint64_t)r, gpr, (uint32_t)h) < drop.thresh ? 0.f : d * drop.scale;
+    }
+    ab2 += d;
+#pragma unroll
+    for (int j = 0; j < kMaxC2; ++j) {
+      if (j < C2) {
+        aw2[j] += d * __ldg(hid + r * C2 + j);
+        const float pj = warp_sum(d * w2[j]);
+        if (lane == 0) red[warp][j] = pj;
+      }
+    }
+    __syncthreads();
+    if (h < C2) {
+      float dh = 0.f;
+      for (int w = 0; w < nw; ++w) dh += red[w][h];
+      // derivative of act(v)*scale expressed through the saved output a = hid
+      if (act == MMFM_ACT_SOFTSIGN) {
+        const float a = hid[r * C2 + h];
+        const float tt = 1.0f - fabsf(a / act_scale);
+        dh *= act_scale * tt * tt;
+      } else {
+        dh *= act_scale;
+      }
+      ab1 += dh;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) aw1[c] += dh * in[r * C + c];
+    }
+    __syncthreads();
+  }
+  atomicAdd(db2 + h, ab2);
+#pragma unroll
+  for (int j = 0; j < kMaxC2; ++j)
+    if (j < C2) atomicAdd(dW2 + h * C2 + j, aw2[j]);
+  if (h < C2) {
+    atomicAdd(db1 + h, ab1);
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) atomicAdd(dW1 + h * C + c, aw1[c]);
+  }
+}
+
+// head forward, C <= 8: warp per row
+__global__ void __launch_bounds__(256) smallc_head_fwd_kernel(const bf16* __restrict__ y, const float* __restrict__ W,
+                                                               const float* __restrict__ bias, float* __restrict__ preds,
+                                                               int R, int H, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
+    float acc[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) acc[c] = 0.f;
+    for (int h0 = lane * 8; h0 < H; h0 += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + r * H + h0));
+      const float2 f[4] = {unpack_bf16x2(v.x), unpack_bf16x2(v.y), unpack_bf16x2(v.z), unpack_bf16x2(v.w)};
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c < C) {
+          const float* w = W + (long long)c * H + h0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[c] += f[j].x * __ldg(w + 2 * j) + f[j].y * __ldg(w + 2 * j + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c < C) {
+        const float s = warp_sum(acc[c]);
+        if (lane == 0) preds[r * C + c] = s + (bias ? bias[c] : 0.f);
+      }
+    }
+  }
+}
+
+// head backward, C <= 8: grid (row chunks, H/256); lane owns 8 consecutive columns of the 256-wide slice
+__global__ void __launch_bounds__(256) smallc_head_bwd_kernel(const bf16* __restrict__ y, const float* __restrict__ W,
+                                                               const bf16* __restrict__ dp, long long lddp,
+                                                               bf16* __restrict__ dy, float* __restrict__ dW,
+                                                               float* __restrict__ db, int R, int H, int C) {
+  __shared__ float red[8][256 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h0 = blockIdx.y * 256 + lane * 8;
+  const bool hok = h0 < H;
+  float w[kMaxC][8], aw[kMaxC][8], ab[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    ab[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w[c][j] = (c < C && hok) ? W[(long long)c * H + h0 + j] : 0.f;
+      aw[c][j] = 0.f;
+    }
+  }
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < R; r += (long long)gridDim.x * 8) {
+    float d[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      d[c] = (c < C) ? __bfloat162float(dp[r * lddp + c]) : 0.f;
+      ab[c] += d[c];
+    }
+    if (hok) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + r * H + h0));
+      const float2 f[4] = {unpack_bf16x2(v.x), unpack_bf16x2(v.y), unpack_bf16x2(v.z), unpack_bf16x2(v.w)};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            aw[c][2 * j] += d[c] * f[j].x;
+            aw[c][2 * j + 1] += d[c] * f[j].y;
+            o[2 * j] += d[c] * w[c][2 * j];
+            o[2 * j + 1] += d[c] * w[c][2 * j + 1];
+          }
+        }
+      }
+      uint4 ov;
+      ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+      ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dy + r * H + h0) = ov;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) {
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = aw[c][j];
+      __syncthreads();
+      const int hh = threadIdx.x;
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) s += red[wv][hh];
+      if (blockIdx.y * 256 + hh < H) atomicAdd(dW + (long long)c * H + blockIdx.y * 256 + hh, s);
+      __syncthreads();
+    }
+  }
+  if (blockIdx.y == 0 && lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) atomicAdd(db + c, ab[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fused masked loss + gradient
+// ------------------------------------------------------------------------------------------------------------
+template <int KIND>
+MMFM_DEVINL void loss_elem(float pr, float tg, float& ell, float& grad) {
+  if (KIND == MMFM_LOSS_POISSON) {
+    const float e = __expf(pr);
+    ell = e - tg * pr;
+    grad = e - tg;
+  } else {
+    const float d = pr - tg;
+    ell = d * d;
+    grad = 2.0f * d;
+  }
+}
+
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ preds, const float* __restrict__ targets,
+                                                    const unsigned char* __restrict__ tok_mask, int S, int off,
+                                                    const float* __restrict__ inv_n, int B, int T, int C,
+                                                    float* __restrict__ partials, bf16* __restrict__ dpreds,
+                                                    long long lddp) {
+  __shared__ float sh[32];
+  const float invn = __ldg(inv_n);
+  float acc = 0.f;
+  if (VEC) {
+    const int cv = C >> 2;
+    const long long total = (long long)B * T * cv;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long r = e / cv;
+      const int c = (int)(e - r * cv) * 4;
+      const long long b = r / T;
+      const int t = (int)(r - b * T);
+      const bool mk = tok_mask[b * S + off + t] != 0;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mk) {
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(preds + r * C + c));
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(targets + r * C + c));
+        float l0, l1, l2, l3;
+        loss_elem<KIND>(pv.x, tv.x, l0, g[0]);
+        loss_elem<KIND>(pv.y, tv.y, l1, g[1]);
+        loss_elem<KIND>(pv.z, tv.z, l2, g[2]);
+        loss_elem<KIND>(pv.w, tv.w, l3, g[3]);
+        acc += (l0 + l1) + (l2 + l3);
+      }
+      uint2 o;
+      o.x = pack_bf16x2(g[0] * invn, g[1] * invn);
+      o.y = pack_bf16x2(g[2] * invn, g[3] * invn);
+      *reinterpret_cast<uint2*>(dpreds + r * lddp + c) = o;
+    }
+  } else {
+    const long long total = (long long)B * T * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long r = e / C;
+      const int c = (int)(e - r * C);
+      const long long b = r / T;
+      const int t = (int)(r - b * T);
+      float g = 0.f;
+      if (tok_mask[b * S + off + t]) {
+        float l;
+        loss_elem<KIND>(preds[e], targets[e], l, g);
+        acc += l;
+      }
+      dpreds[r * lddp + c] = __float2bfloat16_rn(g * invn);
+    }
+  }
+  const float s = block_sum(acc, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int n_partials, int n_mod,
+                                                             const float* __restrict__ inv_n, float* __restrict__ mod_loss,
+                                                             float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float tot = 0.f;
+  for (int m = 0; m < n_mod; ++m) {
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) a += partials[m * n_partials + i];
+    const float s = block_sum(a, sh);
+    if (threadIdx.x == 0) mod_loss[m] = s;
+    tot += s;
+  }
+  if (threadIdx.x == 0) loss[0] = tot * inv_n[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-tensor fp32 -> bf16 cast (weight shadows): one launch for the whole parameter set
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_multi_kernel(const mmfm_cast_item* __restrict__ items, int n_items) {
+  __shared__ float tile[32][33];
+  // locate the item of this tile (tile_start is an exclusive prefix sum)
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].tile_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const mmfm_cast_item it = items[lo];
+  const int tl = blockIdx.x - it.tile_start;
+  const int tcols = (it.cols + 31) >> 5;
+  const int r0 = (tl / tcols) * 32, c0 = (tl % tcols) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  bf16* y = reinterpret_cast<bf16*>(it.dst);
+  bf16* yt = reinterpret_cast<bf16*>(it.dst_t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    float v = 0.f;
+    if (r < it.rows && c < it.cols) {
+      v = it.src[(long long)r * it.ld_src + c];
+      if (y) y[(long long)r * it.ld_dst + c] = __float2bfloat16_rn(v);
+    }
+    tile[ty + i * 8][tx] = v;
+  }
+  if (yt == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;
+    if (r < it.rows && c < it.cols) yt[(long long)c * it.ld_dst_t + r] = __float2bfloat16_rn(tile[tx][ty + i * 8]);
+  }
+}
+
+// x[i] *= *scale (no-op launch when *scale == 1): applies the upstream gradient of the scalar loss
+__global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ x, long long n,
+                                                             const float* __restrict__ scale) {
+  const float s = __ldg(scale);
+  if (s == 1.0f) return;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] *= s;
+}
+
+}  // namespace mmfm
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+using namespace mmfm;
+
+static DropCfg to_drop(const mmfm_dropout* d) {
+  if (d == nullptr || d->thresh == 0u) return DropCfg{nullptr, 0u, 0u, 1.0f};
+  return DropCfg{d->seed, d->site, d->thresh, d->scale};
+}
+static int ew_grid(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" int mmfm_mask_prep(const mmfm_mask_args* a, unsigned char* zero_flags, unsigned char* key_valid,
+                              unsigned char* tok_mask, long long* n_examples, float* inv_n, void* stream) {
+  MMFM_REQUIRE(a && zero_flags && key_valid && tok_mask && n_examples && inv_n, "mmfm_mask_prep: null pointer");
+  MMFM_REQUIRE(a->n_mod >= 1 && a->n_mod <= MMFM_MAX_MOD && a->B > 0 && a->T > 0, "mmfm_mask_prep: bad shape");
+  for (int m = 0; m < a->n_mod; ++m) {
+    MMFM_REQUIRE(a->attn[m] != nullptr, "mmfm_mask_prep: modality %d has no attention mask", m);
+    MMFM_REQUIRE(a->channels[m] > 0, "mmfm_mask_prep: modality %d has no channels", m);
+  }
+  mask_prep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*a, zero_flags, key_valid, tok_mask, n_examples, inv_n);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_embed_assemble(const float* mod_emb_row, const float* pos_embed, const long long* ts, float* emb,
+                                   int B, int T, int S, int off, int H, void* stream) {
+  MMFM_REQUIRE(mod_emb_row && emb && (pos_embed == nullptr || ts), "mmfm_embed_assemble: null pointer");
+  MMFM_REQUIRE(B > 0 && T > 0 && H % 4 == 0 && off >= 0 && off + T <= S, "mmfm_embed_assemble: bad shape");
+  embed_assemble_kernel<<<ew_grid((long long)B * T * (H / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      mod_emb_row, pos_embed, ts, emb, B, T, S, off, H);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_embed_assemble_bwd(const float* g, const float* g2, const long long* ts, float* dpos, float* dmod,
+                                       int B, int T, int S, int off, int H, void* stream) {
+  MMFM_REQUIRE(g && dmod && (dpos == nullptr || ts), "mmfm_embed_assemble_bwd: null pointer");
+  MMFM_REQUIRE(B > 0 && T > 0 && H % 4 == 0 && off >= 0 && off + T <= S, "mmfm_embed_assemble_bwd: bad shape");
+  int chunks = (4 * device_sm_count() + T - 1) / T;
+  if (chunks > B) chunks = B;
+  if (chunks < 1) chunks = 1;
+  const int bchunk = (B + chunks - 1) / chunks;
+  chunks = (B + bchunk - 1) / bchunk;
+  int threads = H / 4;
+  if (threads > 256) threads = 256;
+  threads = (threads + 31) / 32 * 32;
+  embed_assemble_bwd_kernel<<<dim3(T, chunks), threads, 0, (cudaStream_t)stream>>>(g, g2, ts, dpos, dmod, B, T, S, off,
+                                                                                   H, bchunk);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_embed_grad_prep(const float* dx, void* dtok, const unsigned char* row_zero, const mmfm_dropout* drop,
+                                    int B, int T, int S, int off, int H, void* stream) {
+  MMFM_REQUIRE(dx && dtok, "mmfm_embed_grad_prep: null pointer");
+  MMFM_REQUIRE(B > 0 && T > 0 && H % 4 == 0 && off >= 0 && off + T <= S, "mmfm_embed_grad_prep: bad shape");
+  embed_grad_prep_kernel<<<ew_grid((long long)B * T * (H / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      dx, (bf16*)dtok, row_zero, to_drop(drop), B, T, S, off, H);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_smallc_embed_fwd(const float* in, const float* W1, const float* b1, const float* W2, const float* b2,
+                                     const float* emb, float* x, float* hid, const unsigned char* row_zero,
+                                     const mmfm_dropout* drop, float act_scale, int act, int B, int T, int S, int off,
+                                     int C, int H, void* stream) {
+  MMFM_REQUIRE(in && W1 && W2 && emb && x && hid, "mmfm_smallc_embed_fwd: null pointer");
+  MMFM_REQUIRE(C >= 1 && C <= kMaxC, "mmfm_smallc_embed_fwd: C=%d outside [1,%d]", C, kMaxC);
+  MMFM_REQUIRE(act == MMFM_ACT_NONE || act == MMFM_ACT_SOFTSIGN, "mmfm_smallc_embed_fwd: bad act %d", act);
+  MMFM_REQUIRE(B > 0 && T > 0 && H > 0 && off >= 0 && off + T <= S, "mmfm_smallc_embed_fwd: bad shape");
+  smallc_embed_fwd_kernel<<<B * T, 256, 0, (cudaStream_t)stream>>>(in, W1, b1, W2, b2, emb, x, hid, row_zero,
+                                                                   to_drop(drop), act_scale, act, B, T, S, off, C, H);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_smallc_embed_bwd(const float* in, const float* hid, const float* W2, const float* dx,
+                                     const unsigned char* row_zero, const mmfm_dropout* drop, float act_scale, int act,
+                                     float* dW1, float* db1, float* dW2, float* db2, int B, int T, int S, int off, int C,
+                                     int H, void* stream) {
+  MMFM_REQUIRE(in && hid && W2 && dx && dW1 && db1 && dW2 && db2, "mmfm_smallc_embed_bwd: null pointer");
+  MMFM_REQUIRE(C >= 1 && C <= kMaxC, "mmfm_smallc_embed_bwd: C=%d outside [1,%d]", C, kMaxC);
+  MMFM_REQUIRE(H % 32 == 0 && H <= 1024, "mmfm_smallc_embed_bwd: H=%d must be a multiple of 32 and <= 1024", H);
+  MMFM_REQUIRE(B > 0 && T > 0 && off >= 0 && off + T <= S, "mmfm_smallc_embed_bwd: bad shape");
+  const long long R = (long long)B * T;
+  int ctas = 2 * device_sm_count();
+  int rows_per_cta = (int)((R + ctas - 1) / ctas);
+  if (rows_per_cta < 16) rows_per_cta = 16;
+  ctas = (int)((R + rows_per_cta - 1) / rows_per_cta);
+  smallc_embed_bwd_kernel<<<ctas, H, 0, (cudaStream_t)stream>>>(in, hid, W2, dx, row_zero, to_drop(drop), act_scale, act,
+                                                                dW1, db1, dW2, db2, B, T, S, off, C, H, rows_per_cta);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_smallc_head_fwd(const void* y, const float* W, const float* b, float* preds, int R, int H, int C,
+                                    void* stream) {
+  MMFM_REQUIRE(y && W && preds, "mmfm_smallc_head_fwd: null pointer");
+  MMFM_REQUIRE(C >= 1 && C <= kMaxC && R > 0 && H % 8 == 0, "mmfm_smallc_head_fwd: bad shape R=%d H=%d C=%d", R, H, C);
+  smallc_head_fwd_kernel<<<ew_grid(R, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)y, W, b, preds, R, H, C);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_smallc_head_bwd(const void* y, const float* W, const void* dpreds, long long lddp, void* dy,
+                                    float* dW, float* db, int R, int H, int C, void* stream) {
+  MMFM_REQUIRE(y && W && dpreds && dy && dW && db, "mmfm_smallc_head_bwd: null pointer");
+  MMFM_REQUIRE(C >= 1 && C <= kMaxC && R > 0 && H % 8 == 0, "mmfm_smallc_head_bwd: bad shape R=%d H=%d C=%d", R, H, C);
+  int gx = (R + 63) / 64;
+  const int cap = 2 * device_sm_count();
+  if (gx > cap) gx = cap;
+  smallc_head_bwd_kernel<<<dim3(gx, (H + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, W, (const bf16*)dpreds, lddp, (bf16*)dy, dW, db, R, H, C);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_loss_fwd_bwd(const float* preds, const float* targets, const unsigned char* tok_mask, int S, int off,
+                                 const float* inv_n, int kind, int B, int T, int C, float* partials, int n_partials,
+                                 void* dpreds, long long lddp, void* stream) {
+  MMFM_REQUIRE(preds && targets && tok_mask && inv_n && partials && dpreds, "mmfm_loss_fwd_bwd: null pointer");
+  MMFM_REQUIRE(kind == MMFM_LOSS_POISSON || kind == MMFM_LOSS_MSE, "mmfm_loss_fwd_bwd: bad loss kind %d", kind);
+  MMFM_REQUIRE(B > 0 && T > 0 && C > 0 && n_partials > 0 && lddp >= C, "mmfm_loss_fwd_bwd: bad shape");
+  const bool vec = (C % 4 == 0) && (lddp % 4 == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16* dp = (bf16*)dpreds;
+#define LOSS(K, V) loss_kernel<K, V><<<n_partials, 256, 0, st>>>(preds, targets, tok_mask, S, off, inv_n, B, T, C, partials, dp, lddp)
+  if (kind == MMFM_LOSS_POISSON) { if (vec) LOSS(MMFM_LOSS_POISSON, true); else LOSS(MMFM_LOSS_POISSON, false); }
+  else { if (vec) LOSS(MMFM_LOSS_MSE, true); else LOSS(MMFM_LOSS_MSE, false); }
+#undef LOSS
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_loss_finalize(const float* partials, int n_partials, int n_mod, const float* inv_n, float* mod_loss,
+                                  float* loss, void* stream) {
+  MMFM_REQUIRE(partials && inv_n && mod_loss && loss && n_partials > 0 && n_mod > 0, "mmfm_loss_finalize: bad arguments");
+  loss_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, n_partials, n_mod, inv_n, mod_loss, loss);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_cast_bf16_multi(const mmfm_cast_item* items_dev, int n_items, int total_tiles, void* stream) {
+  MMFM_REQUIRE(items_dev && n_items > 0 && total_tiles > 0, "mmfm_cast_bf16_multi: bad arguments");
+  cast_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(items_dev, n_items);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stream) {
+  MMFM_REQUIRE(x && scale_dev && n > 0, "mmfm_scale_inplace: bad arguments");
+  MMFM_REQUIRE(((uintptr_t)x & 15) == 0, "mmfm_scale_inplace: buffer must be 16-byte aligned");
+  scale_inplace_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

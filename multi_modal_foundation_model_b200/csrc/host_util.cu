@@ -1,4 +1,5 @@
 #include "host_util.h"
+#include "../../include/mmfm_b200.h"
 
 #include <stdarg.h>
 
@@ -70,3 +71,12 @@ int device_sm_count() {
 }
 
 }  // namespace mmfm
+
+extern "C" const char* mmfm_last_error(void) { return mmfm::get_error(); }
+extern "C" int mmfm_abi_version(void) { return MMFM_ABI_VERSION; }
+extern "C" int mmfm_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}

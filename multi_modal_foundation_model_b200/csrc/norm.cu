@@ -1,0 +1,261 @@
+// LayerNorm forward / backward (nn.LayerNorm(H), eps 1e-5, affine): bandwidth kernels.
+//
+// Replaces ATen's vectorized_layer_norm_kernel / layer_norm_backward under every LayerNorm of the reference path
+// (encoder_embeddings.py:98-100,112,114; decoder_embeddings.py:116-126,141-145; mm.py:72,77,202,212).
+//
+// One warp owns one row: the fp32 row is read once with 16-byte loads into registers (H <= 2048 and H % 128 == 0
+// take the register path; other widths re-read through L1), mean/variance are warp-shuffle reductions, the bf16
+// output is written with 8-byte stores.  The backward kernel fuses the residual-gradient add, the optional
+// dropout-masked bf16 copy that feeds the next dgrad GEMM, and the dgamma/dbeta column sums (register partials per
+// lane -> shared-memory reduction per CTA -> one red.global per column per CTA).
+#include "common.cuh"
+#include "host_util.h"
+#include "../../include/mmfm_b200.h"
+
+namespace mmfm {
+
+constexpr int kLnWarps = 8;  // rows per CTA pass
+
+MMFM_DEVINL long long ln_out_row(long long r, int modmajor_T, int S, long long BT) {
+  if (modmajor_T <= 0) return r;
+  const long long b = r / S;
+  const int s = (int)(r - b * S);
+  const int m = s / modmajor_T;
+  return (long long)m * BT + b * modmajor_T + (s - m * modmajor_T);
+}
+
+// NV = number of float4 chunks per lane (H = 128 * NV); NV == 0 -> generic width (H % 4 == 0), re-reading x.
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta,
+                                                                       bf16* __restrict__ y, float* __restrict__ mean,
+                                                                       float* __restrict__ rstd, int R, int H,
+                                                                       float eps, int modmajor_T, int S) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
+  const float invH = 1.0f / (float)H;
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
+    const float* xr = x + r * H;
+    bf16* yr = y + ln_out_row(r, modmajor_T, S, BT) * H;
+    if constexpr (NV > 0) {
+      float4 v[NV];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(xr) + lane + 32 * j);
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+      const float mu = warp_sum(s) * invH;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float a = v[j].x - mu, b = v[j].y - mu, c = v[j].z - mu, d = v[j].w - mu;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rs = rsqrtf(warp_sum(q) * invH + eps);
+      if (lane == 0) {
+        mean[r] = mu;
+        rstd[r] = rs;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+        uint2 o;
+        o.x = pack_bf16x2((v[j].x - mu) * rs * g.x + b.x, (v[j].y - mu) * rs * g.y + b.y);
+        o.y = pack_bf16x2((v[j].z - mu) * rs * g.z + b.z, (v[j].w - mu) * rs * g.w + b.w);
+        reinterpret_cast<uint2*>(yr)[lane + 32 * j] = o;
+      }
+    } else {
+      float s = 0.f;
+      for (int c = lane * 4; c < H; c += 128) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+        s += (t.x + t.y) + (t.z + t.w);
+      }
+      const float mu = warp_sum(s) * invH;
+      float q = 0.f;
+      for (int c = lane * 4; c < H; c += 128) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+        const float a = t.x - mu, b = t.y - mu, cc = t.z - mu, d = t.w - mu;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+      const float rs = rsqrtf(warp_sum(q) * invH + eps);
+      if (lane == 0) {
+        mean[r] = mu;
+        rstd[r] = rs;
+      }
+      for (int c = lane * 4; c < H; c += 128) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        uint2 o;
+        o.x = pack_bf16x2((t.x - mu) * rs * g.x + b.x, (t.y - mu) * rs * g.y + b.y);
+        o.y = pack_bf16x2((t.z - mu) * rs * g.z + b.z, (t.w - mu) * rs * g.w + b.w);
+        *reinterpret_cast<uint2*>(yr + c) = o;
+      }
+    }
+  }
+}
+
+// dx = dres + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat));  dgamma += sum dy*xhat; dbeta += sum dy
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* dres, float* dx,
+    bf16* __restrict__ dxb, DropCfg drop, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int H,
+    int modmajor_T, int S) {
+  static_assert(NV > 0, "register path only");
+  __shared__ float red[kLnWarps][NV * 128 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
+  const float invH = 1.0f / (float)H;
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  const uint32_t gpr = (uint32_t)((H + 15) >> 4);
+
+  float4 gam[NV], accg[NV], accb[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    gam[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    accg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    accb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
+    const float* xr = x + r * H;
+    const bf16* dyr = dy + ln_out_row(r, modmajor_T, S, BT) * H;
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    float4 xh[NV], gd[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + lane + 32 * j);
+      const uint2 dv = __ldg(reinterpret_cast<const uint2*>(dyr) + lane + 32 * j);
+      const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      accb[j].x += d01.x; accb[j].y += d01.y; accb[j].z += d23.x; accb[j].w += d23.y;
+      accg[j].x += d01.x * xh[j].x; accg[j].y += d01.y * xh[j].y;
+      accg[j].z += d23.x * xh[j].z; accg[j].w += d23.y * xh[j].w;
+      gd[j] = make_float4(d01.x * gam[j].x, d01.y * gam[j].y, d23.x * gam[j].z, d23.y * gam[j].w);
+      s1 += (gd[j].x + gd[j].y) + (gd[j].z + gd[j].w);
+      s2 += (gd[j].x * xh[j].x + gd[j].y * xh[j].y) + (gd[j].z * xh[j].z + gd[j].w * xh[j].w);
+    }
+    const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 o;
+      o.x = rs * (gd[j].x - m1 - xh[j].x * m2);
+      o.y = rs * (gd[j].y - m1 - xh[j].y * m2);
+      o.z = rs * (gd[j].z - m1 - xh[j].z * m2);
+      o.w = rs * (gd[j].w - m1 - xh[j].w * m2);
+      if (dres) {
+        const float4 dr = reinterpret_cast<const float4*>(dres + r * H)[lane + 32 * j];
+        o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
+      }
+      if (dx) reinterpret_cast<float4*>(dx + r * H)[lane + 32 * j] = o;
+      if (dxb) {
+        if (drop.thresh != 0u) {
+          const int c = (lane + 32 * j) * 4;
+          const uint4 w = drop_bytes16(seed, drop.site, (uint64_t)r, gpr, (uint32_t)(c >> 4));
+          const int b0 = c & 15;
+          o.x = (drop_byte(w, b0) < drop.thresh) ? 0.f : o.x * drop.scale;
+          o.y = (drop_byte(w, b0 + 1) < drop.thresh) ? 0.f : o.y * drop.scale;
+          o.z = (drop_byte(w, b0 + 2) < drop.thresh) ? 0.f : o.z * drop.scale;
+          o.w = (drop_byte(w, b0 + 3) < drop.thresh) ? 0.f : o.w * drop.scale;
+        }
+        uint2 p;
+        p.x = pack_bf16x2(o.x, o.y);
+        p.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dxb + r * H)[lane + 32 * j] = p;
+      }
+    }
+  }
+  // CTA reduction of the column partials, then one atomic per column per CTA
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 a = pass == 0 ? accg[j] : accb[j];
+      float* dst = &red[warp][(lane + 32 * j) * 4];
+      dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+    }
+    __syncthreads();
+    float* out = pass == 0 ? dgamma : dbeta;
+    if (out) {
+      for (int c = threadIdx.x; c < H; c += kLnWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+        atomicAdd(out + c, s);
+      }
+    }
+  }
+}
+
+}  // namespace mmfm
+
+using namespace mmfm;
+
+static int ln_grid(int R) {
+  const int want = (R + kLnWarps - 1) / kLnWarps;
+  const int cap = device_sm_count() * 8;
+  return want < cap ? want : cap;
+}
+
+extern "C" int mmfm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, int R, int H, float eps, int modmajor_T, int S, void* stream) {
+  MMFM_REQUIRE(x && gamma && beta && y && mean && rstd, "mmfm_layernorm_fwd: null pointer");
+  MMFM_REQUIRE(R > 0 && H > 0 && H % 4 == 0, "mmfm_layernorm_fwd: bad shape R=%d H=%d (H must be a multiple of 4)", R, H);
+  MMFM_REQUIRE(modmajor_T <= 0 || (S > 0 && S % modmajor_T == 0 && R % S == 0),
+               "mmfm_layernorm_fwd: modality-major remap needs S %% T == 0 and R %% S == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(R);
+#define LN_FWD(NV) \
+  layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, (bf16*)y, mean, rstd, R, H, eps, modmajor_T, S)
+  switch (H) {
+    case 128: LN_FWD(1); break;
+    case 256: LN_FWD(2); break;
+    case 512: LN_FWD(4); break;
+    case 1024: LN_FWD(8); break;
+    default: LN_FWD(0); break;
+  }
+#undef LN_FWD
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, const float* dres, float* dx, void* dxb,
+                                  const mmfm_dropout* drop, float* dgamma, float* dbeta, int R, int H, int modmajor_T,
+                                  int S, void* stream) {
+  MMFM_REQUIRE(dy && x && mean && rstd && gamma, "mmfm_layernorm_bwd: null pointer");
+  MMFM_REQUIRE(dx || dxb, "mmfm_layernorm_bwd: no output requested");
+  MMFM_REQUIRE(R > 0 && (H == 128 || H == 256 || H == 512 || H == 1024),
+               "mmfm_layernorm_bwd: hidden size %d not supported (128/256/512/1024)", H);
+  MMFM_REQUIRE(modmajor_T <= 0 || (S > 0 && S % modmajor_T == 0 && R % S == 0),
+               "mmfm_layernorm_bwd: modality-major remap needs S %% T == 0 and R %% S == 0");
+  DropCfg dc{nullptr, 0u, 0u, 1.0f};
+  if (drop && drop->thresh != 0u) {
+    MMFM_REQUIRE(drop->seed != nullptr && drop->thresh < 256u, "mmfm_layernorm_bwd: bad dropout config");
+    dc = DropCfg{drop->seed, drop->site, drop->thresh, drop->scale};
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // fewer, fatter CTAs than the forward: every CTA ends with 2*H atomics
+  int grid = (R + kLnWarps * 8 - 1) / (kLnWarps * 8);
+  const int cap = device_sm_count() * 4;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+#define LN_BWD(NV)                                                                                             \
+  layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const bf16*)dy, x, mean, rstd, gamma, dres, dx, \
+                                                            (bf16*)dxb, dc, dgamma, dbeta, R, H, modmajor_T, S)
+  switch (H) {
+    case 128: LN_BWD(1); break;
+    case 256: LN_BWD(2); break;
+    case 512: LN_BWD(4); break;
+    default: LN_BWD(8); break;
+  }
+#undef LN_BWD
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

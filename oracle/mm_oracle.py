@@ -77,12 +77,13 @@ class _Drop:
     def __init__(self, seed: Optional[int]):
         self.seed = seed
 
-    def __call__(self, x: torch.Tensor, p: float, site: int) -> torch.Tensor:
+    def __call__(self, x: torch.Tensor, p: float, site: int, prob_layout: bool = False) -> torch.Tensor:
         if self.seed is None or p <= 0.0:
             return x
         cols = x.shape[-1]
         rows = x.numel() // cols
-        m = torch.from_numpy(px.keep_mask(self.seed, site, rows, cols, p)).to(x.dtype)
+        fn = px.prob_keep_mask if prob_layout else px.keep_mask
+        m = torch.from_numpy(fn(self.seed, site, rows, cols, p)).to(x.dtype)
         return x * m.reshape(x.shape)
 
 
@@ -130,7 +131,7 @@ def attention(P, prefix: str, spec: OracleSpec, x_q, x_kv, allowed, drop: _Drop,
     s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(d))
     s = s.masked_fill(~allowed[:, None, :, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
-    p = drop(p, spec.dropout, site_prob)          # rows = ((b*nh+h)*Sq+i), cols = Sk
+    p = drop(p, spec.dropout, site_prob, prob_layout=True)   # rows = ((b*nh+h)*Sq+i), cols = Sk
     o = (p @ v).transpose(1, 2).reshape(B, Sq, H)
     o = drop(o, spec.dropout, site_out)
     return _linear(P, prefix + ".out_proj", o)

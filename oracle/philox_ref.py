@@ -11,6 +11,16 @@ activations/gradients can be checked against the oracle with identical masks:
 * one call yields 16 bytes = 16 consecutive elements of one row:
   group = row * ceil(cols/16) + col // 16, byte index = col % 16 (little-endian inside each word);
 * element is DROPPED iff byte < round(p * 256); kept elements are scaled by 256 / (256 - round(p*256)).
+
+The dropout on the attention probabilities (``F.scaled_dot_product_attention(dropout_p=...)`` in the reference)
+uses an interleaved variant so that one generator call covers the 16 elements one thread of the attention kernel
+owns inside a 64-column block (``csrc/attention.cu``): for field row r (= (b*n_heads+h)*Sq + i) and key column j,
+``blk = j // 64``, ``n = (j % 64) // 8``, ``q = (j % 8) // 2``, ``e = j % 2``; the call has
+counter = (g_lo, g_hi, site, 1) with ``g = (r * ceil(Sk/64) + blk) * 4 + q`` and the element reads byte ``2*n + e``.
+
+Deviation from the reference, stated once: probabilities are quantised to 1/256 (0.4 -> 102/256 = 0.3984,
+0.2 -> 51/256 = 0.1992) and the survivors are rescaled by the matching 256/(256-t), so the estimator stays
+unbiased; bit-level agreement with PyTorch's own Philox offsets is impossible for a foreign kernel.
 """
 from __future__ import annotations
 
@@ -54,6 +64,27 @@ def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = PHILOX_ROUNDS):
         k0 = (k0 + _W0) & 0xFFFFFFFF
         k1 = (k1 + _W1) & 0xFFFFFFFF
     return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def prob_random_bytes(seed: int, site: int, rows: int, cols: int) -> np.ndarray:
+    """(rows, cols) uint8 field of an attention-probability dropout site (interleaved layout, see header)."""
+    nblk = (cols + 63) // 64
+    g = np.arange(rows * nblk * 4, dtype=np.uint64)
+    c0 = (g & _MASK32).astype(np.uint32)
+    c1 = (g >> np.uint64(32)).astype(np.uint32)
+    c2 = np.full_like(c0, np.uint32(site & 0xFFFFFFFF))
+    c3 = np.ones_like(c0)
+    w = philox4x32(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    by = np.stack(w, axis=1).view(np.uint8).reshape(rows, nblk, 4, 8, 2)   # (row, blk, q, n, e)
+    by = by.transpose(0, 1, 3, 2, 4).reshape(rows, nblk * 64)              # column = blk*64 + n*8 + q*2 + e
+    return by[:, :cols]
+
+
+def prob_keep_mask(seed: int, site: int, rows: int, cols: int, p: float) -> np.ndarray:
+    if p <= 0.0:
+        return np.ones((rows, cols), dtype=np.float32)
+    by = prob_random_bytes(seed, site, rows, cols)
+    return (by >= drop_threshold(p)).astype(np.float32) * np.float32(keep_scale(p))
 
 
 def random_bytes(seed: int, site: int, rows: int, cols: int) -> np.ndarray:
