@@ -1,0 +1,6 @@
+"""B200-native forward/backward of the masked multi-modal encoder/decoder (drop-in for the reference's
+``multi_modal.mm.MultiModal``).  See DESIGN.md."""
+from .config import DotDict, default_model_config, scaled_model_config  # noqa: F401
+from .masker import Masker  # noqa: F401
+from .model import (DecoderEmbedding, EncoderEmbedding, MultiModal, MultiModalOutput, build_model,  # noqa: F401
+                    convert)

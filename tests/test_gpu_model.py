@@ -1,0 +1,148 @@
+"""GPU parity of the whole forward+backward step (engine.py -> libmmfm_b200.so) against
+ (a) the golden fixtures produced by the unmodified reference, and
+ (b) the CPU oracle (oracle/mm_oracle.py, itself pinned to the reference by tests/test_oracle_golden.py)
+on the same seeded inputs.
+
+Tolerances (bf16 tensor-core operands, fp32 accumulation / residual stream / loss):
+  masks, counts: bit-exact;  loss: rel 2e-3;  predictions: abs 3e-2;  gradients: rel-L2 3e-2 and cosine >= 0.999.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import cosine, load_small, oracle_batch, oracle_params, rel_l2, small_config
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL, PRED_ATOL, GRAD_RL2, GRAD_COS = 2e-3, 3e-2, 3e-2, 0.999
+
+
+def _mod_dict(spikes, target, attn, ts, masks, dev="cuda"):
+    md = {}
+    for i, (m, x) in enumerate((("ap", spikes), ("behavior", target))):
+        md[m] = dict(inputs=x.to(dev).clone(), targets=x.to(dev).clone(), inputs_attn_mask=attn.to(dev),
+                     inputs_timestamp=ts.to(dev), inputs_modality=torch.tensor(i, device=dev), masking_mode=None,
+                     eval_mask=None if masks is None else masks[m].to(dev)[:, :, None].contiguous(),
+                     inputs_regions=np.array([["CA1"] * x.shape[2]] * x.shape[0]))
+    return md
+
+
+def _check_grads(model, ref_grads, what):
+    worst = (0.0, None)
+    for n, p in model.named_parameters():
+        g_ref = ref_grads[n]
+        assert p.grad is not None, n
+        if g_ref.norm() < 1e-6:
+            assert p.grad.float().norm().item() < 1e-4, n
+            continue
+        r, c = rel_l2(p.grad.cpu(), g_ref), cosine(p.grad.cpu(), g_ref)
+        if r > worst[0]:
+            worst = (r, n)
+        assert r < GRAD_RL2 and c > GRAD_COS, f"{what}: {n} rel-L2 {r:.4g} cosine {c:.6f}"
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["token_masking", "encoding", "decoding"])
+def test_step_matches_reference_golden(mode):
+    from multi_modal_foundation_model_b200.model import build_model
+    z, W = load_small()
+    model = build_model(40, 2, small_config())
+    model.load_state_dict(W)
+    model = model.cuda().eval()
+    masks = {m: torch.from_numpy(z[f"{mode}/mask/{m}"]) for m in ("ap", "behavior")}
+    md = _mod_dict(torch.from_numpy(z["in/spikes"]), torch.from_numpy(z["in/target"]), torch.from_numpy(z["in/attn"]),
+                   torch.from_numpy(z["in/ts"]), masks)
+    out = model(md)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    ref_loss = float(z[f"{mode}/loss"])
+    assert abs(out.loss.item() - ref_loss) <= LOSS_RTOL * abs(ref_loss), (out.loss.item(), ref_loss)
+    for m in ("ap", "behavior"):
+        assert int(out.mod_n_examples[m]) == int(z[f"{mode}/n/{m}"])
+        rl = float(z[f"{mode}/mod_loss/{m}"])
+        assert abs(out.mod_loss[m].item() - rl) <= 3e-3 * abs(rl) + 1e-3
+        err = np.abs(out.mod_preds[m].detach().cpu().numpy() - z[f"{mode}/preds/{m}"]).max()
+        assert err < PRED_ATOL, (m, err)
+    if mode == "token_masking":
+        ref_grads = {n: torch.from_numpy(z[f"{mode}/grad/{n}"]) for n, _ in model.named_parameters()}
+        _check_grads(model, ref_grads, mode)
+    else:
+        for n, p in model.named_parameters():
+            gn = float(z[f"{mode}/gnorm/{n}"])
+            assert abs(p.grad.double().norm().item() - gn) <= 3e-2 * gn + 1e-5, n
+
+
+@pytest.mark.parametrize("cfg_kw,N,B,pad,dropout", [
+    (dict(), 96, 3, 10, False),                                  # default mm.yaml: 5+5 layers, H 256, 8 heads
+    (dict(), 668, 2, 0, False),                                  # yaml n_channels (row pitch not 16-byte aligned)
+    (dict(decoder_causal_mask=True), 64, 2, 0, False),
+    (dict(decoder_sep_mask=True), 64, 2, 20, False),
+    (dict(), 96, 3, 10, True),                                   # train(): all six dropout sites on
+    (dict(hidden_size=512, n_heads=8, inter_size=1024, n_layers=2), 128, 2, 0, True),   # d_head 64
+])
+def test_step_matches_oracle(cfg_kw, N, B, pad, dropout):
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    cfg = default_model_config(**cfg_kw)
+    torch.manual_seed(11)
+    model = build_model(N, 2, cfg)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    W = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    model.train(dropout)
+    batch = make_batch(B, N, 2, 100, step=2, pad_bins=pad)
+    g = torch.Generator().manual_seed(5)
+    masks = {m: (torch.rand(B, 100, generator=g) < 0.3).long() for m in ("ap", "behavior")}
+    md = _mod_dict(batch["spikes_data"], batch["target"], batch["time_attn_mask"], batch["spikes_timestamps"], masks)
+    out = model(md)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    seed = None
+    if dropout:
+        seed = int(model.engine().last_plan.seed.item()) & 0xFFFFFFFFFFFFFFFF
+    spec = orc.OracleSpec.from_config(cfg, ["ap", "behavior"])
+    ob = {m: dict(inputs=x, targets=x, attn_mask=batch["time_attn_mask"], timestamp=batch["spikes_timestamps"],
+                  mask=masks[m] & batch["time_attn_mask"])
+          for m, x in (("ap", batch["spikes_data"]), ("behavior", batch["target"]))}
+    ref, grads = orc.forward_backward(oracle_params(W), spec, ob, dropout_seed=seed)
+    assert abs(out.loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (out.loss.item(), ref.loss.item())
+    for m in ("ap", "behavior"):
+        assert int(out.mod_n_examples[m]) == int(ref.mod_n_examples[m])
+        err = (out.mod_preds[m].detach().cpu() - ref.mod_preds[m].detach()).abs().max().item()
+        assert err < PRED_ATOL * (2 if dropout else 1), (m, err)
+    worst = _check_grads(model, grads, "oracle")
+    print("worst grad rel-L2:", worst)
+
+
+def test_masker_path_and_grad_accumulation():
+    """token_masking through the host Masker (eval_mask=None) + two backward passes accumulate like autograd."""
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch, make_mod_dict
+    torch.manual_seed(0)
+    model = build_model(48, 2, small_config()).cuda().eval()
+    batch = make_batch(4, 48, 2, 100, step=3)
+    torch.manual_seed(77)
+    md = make_mod_dict(batch, ["ap", "behavior"], "token_masking", device="cuda")
+    out = model(md)
+    # same seed -> the same (B,T) Bernoulli field as the reference Masker would draw first
+    torch.manual_seed(77)
+    torch.bernoulli(torch.tensor(0.0))
+    m_ap = torch.bernoulli(torch.full((4, 100), 0.3)).long()
+    assert int(out.mod_n_examples["ap"]) == int(m_ap.sum()) * 48
+    out.loss.backward()
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters()}
+    torch.manual_seed(77)
+    md = make_mod_dict(batch, ["ap", "behavior"], "token_masking", device="cuda")
+    out2 = model(md)
+    (0.5 * out2.loss).backward()                                   # accumulates 0.5 * g on top of g
+    for n, p in model.named_parameters():
+        assert torch.allclose(p.grad, 1.5 * g1[n], rtol=1e-3, atol=1e-6), n
+    model.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        out3 = model(make_mod_dict(batch, ["ap", "behavior"], "decoding", device="cuda"))
+    assert out3.loss.requires_grad is False and torch.isfinite(out3.loss)

@@ -77,7 +77,8 @@ def test_layernorm_bwd_dropout_copy():
     seed = torch.tensor([99], dtype=torch.int64, device="cuda")
     ops.layernorm_bwd(dy, x, mean, rstd, g, None, dx, dxb, ops.DropSpec(seed, 5, 0.4), None, None, R=R, H=H)
     keep = torch.from_numpy(px.keep_mask(99, 5, R, H, 0.4)).cuda()
-    assert (dxb.float() - dx * keep).abs().max().item() < 3e-2
+    ref = dx * keep
+    assert ((dxb.float() - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-6).all()   # one bf16 rounding
 
 
 def test_mask_prep_and_embed():

@@ -1,0 +1,118 @@
+"""CPU: host-side logic -- Masker bit-exactness against the reference's masks, initial-weight parity of the module
+classes, state_dict key parity, pickling, the C ABI export list, config restatement."""
+import ctypes
+import io
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import _reference as ref
+from _util import GOLDEN, small_config
+from multi_modal_foundation_model_b200 import _lib
+from multi_modal_foundation_model_b200.config import default_model_config
+from multi_modal_foundation_model_b200.masker import Masker
+from multi_modal_foundation_model_b200.model import build_model
+
+
+def test_masker_bit_exact_against_reference_masks():
+    z = np.load(os.path.join(GOLDEN, "masker.npz"))
+    n = len([k for k in z.files if k.endswith("/meta")])
+    for i in range(n):
+        seed, B, T, C, r1000 = [int(v) for v in z[f"case{i}/meta"]]
+        cfg = default_model_config(mask_ratio=r1000 / 1000.0)
+        mk = Masker(cfg["masker"])
+        torch.manual_seed(seed)
+        regions = np.array([["CA1"] * C] * B)
+        for call in range(3):
+            torch.poisson(torch.full((B, T, C), 0.3))            # the fixture generator drew its inputs in between
+            m = mk.sample_token_mask((B, T, C), "cpu", regions)
+            assert m.dtype == torch.int64 and m.shape == (B, T)
+            assert np.array_equal(m.numpy().astype(np.int8), z[f"case{i}/masks"][call]), (i, call)
+
+
+def test_masker_early_outs_and_forward_shape():
+    cfg = default_model_config(mask_ratio=0.0)
+    mk = Masker(cfg["masker"])
+    x = torch.ones(2, 10, 3)
+    y, m = mk(x, None)
+    assert m.shape == (2, 10, 3) and m.sum() == 0 and y is x
+    cfg = default_model_config(mask_ratio=0.3)
+    mk = Masker(cfg["masker"])
+    mk.force_active = False
+    mk.eval()
+    assert mk.sample_token_mask((2, 10, 3), "cpu").sum() == 0
+    mk.mode = "neuron"
+    mk.train()
+    with pytest.raises(NotImplementedError):
+        mk.sample_token_mask((2, 10, 3), "cpu")
+
+
+def test_initial_weights_match_reference_seed42():
+    z = np.load(os.path.join(GOLDEN, "init_default.npz"))
+    torch.manual_seed(42)
+    model = build_model(64, 2, default_model_config())
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == sorted(z.files)
+    for k, v in sd.items():
+        got = np.array([v.double().sum().item(), v.double().abs().sum().item(), float(v.flatten()[0])])
+        assert np.allclose(got, z[k], rtol=1e-12, atol=1e-12), k
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference tree not mounted")
+def test_state_dict_keys_match_reference_live():
+    cfg = ref.load_config()
+    rm = ref.build_reference_model(cfg, 32, 2)
+    ours = build_model(32, 2, cfg["model"])          # accepts the reference's own DictConfig
+    assert list(ours.state_dict().keys()) == list(rm.state_dict().keys())
+    ours.load_state_dict(rm.state_dict())
+    assert ours.decoder_embeddings["ap"].embedder.mod_emb is ours.encoder_embeddings["ap"].embedder.mod_emb
+
+
+def test_model_pickles_without_engine_handles():
+    model = build_model(16, 2, small_config())
+    buf = io.BytesIO()
+    torch.save({"model": model, "epoch": 3}, buf)          # trainer/base.py:302-308
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)["model"]
+    assert m2._engine is None and m2.masker.ratio == model.masker.ratio
+    assert m2.mod_to_indx == {"ap": 0, "behavior": 1}
+
+
+def test_cpu_model_refuses_to_run():
+    from multi_modal_foundation_model_b200._lib import MmfmError
+    model = build_model(16, 2, small_config())
+    with pytest.raises(MmfmError):
+        model({"ap": {}, "behavior": {}})
+
+
+def test_library_exports_every_declared_symbol():
+    _lib.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "mmfm_b200.h")).read()
+    declared = set(re.findall(r"\b(mmfm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().mmfm_abi_version() == 1
+    # no compute call without a GPU: bad arguments are rejected on the host with a message
+    assert _lib.lib().mmfm_gemm_tn(None, None) == -1
+    assert b"null args" in _lib.lib().mmfm_last_error()
+
+
+@pytest.mark.skipif(not ref.available(), reason="reference tree not mounted")
+def test_default_config_restates_mm_yaml():
+    cfg = ref.load_config()["model"]
+    ours = default_model_config()
+
+    def walk(a, b, path=""):
+        for k, v in a.items():
+            assert k in b, path + k
+            if isinstance(v, dict):
+                walk(v, b[k], path + k + ".")
+            else:
+                assert b[k] == v, (path + k, b[k], v)
+    walk(dict(cfg), ours)
