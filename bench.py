@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- train trials/sec (forward + backward) of the masked multi-modal encoder/decoder on B200.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (hand-written sm_100a kernels via the C ABI)
+    python bench.py --impl reference ...                     the reference algorithm's CPU path (oracle port) on the
+                                                             box's host cores, same workload / metric / unit
+
+Workload (BASELINE.json configs[1]): mm.yaml default MultiModal (5+5 layers, H 256, 8 heads, MLP 512), modalities
+ap (N=668 spike channels, the yaml's n_channels) + behavior (wheel speed, whisker motion energy), T=100 bins,
+B=256 trials per GPU, model.train() (all six dropout sites + masking active), training mode cycling through
+encoding / decoding / token_masking as ``--mixed_training`` does (trainer/base.py:189-190), synthetic IBL-shaped
+data (multi_modal_foundation_model_b200/synthetic.py), random-init weights at seed 42.  One step = one
+``model(mod_dict)`` + ``loss.backward()`` (optimizer excluded, as in the metric's definition).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is produced.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODES = ("encoding", "decoding", "token_masking")
+METRIC = "train trials/sec fwd+bwd"
+UNIT = "trials/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="trials per GPU per step")
+    ap.add_argument("--neurons", type=int, default=668)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="trials per step of the CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity configuration)")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": "configs[1]: multi-modal encoder/decoder (ap spikes + wheel speed + whisker motion energy), "
+                    "mm.yaml default model 5+5 layers H256 8 heads MLP512, single synthetic IBL-shaped session",
+        "neurons": a.neurons, "behaviors": 2, "time_bins": 100, "tokens_per_trial": 200,
+        "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus,
+        "mode": "eval() (dropout off)" if a.eval_mode else "train() (dropout 0.2/0.4 + masker active)",
+        "training_modes": "encoding/decoding/token_masking cycled",
+        "parallelism": f"dp{n_gpus}",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(a, seconds: float, min_steps: int = 2, fixed_steps: int = 0, warmup: int = 1):
+    """The reference algorithm on the host CPU: oracle/mm_oracle.py (PyTorch fp32 restatement pinned to the
+    reference by tests/golden) forward + backward, all host threads.  Returns (trials/s, cores, steps, s/step)."""
+    import torch
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = default_model_config()
+    torch.manual_seed(42)
+    model = build_model(a.neurons, 2, cfg)
+    P = {k: v.detach() for k, v in model.state_dict().items()}
+    for k in list(P):
+        if k.startswith("decoder_embeddings.") and k.endswith("mod_emb.weight"):
+            P[k] = P[k.replace("decoder_embeddings.", "encoder_embeddings.")]
+    spec = orc.OracleSpec.from_config(cfg, ["ap", "behavior"])
+    B = a.cpu_batch
+
+    def one(step):
+        batch = make_batch(B, a.neurons, 2, 100, step=step)
+        attn = batch["time_attn_mask"]
+        mode = MODES[step % 3]
+        g = torch.Generator().manual_seed(step)
+        ob = {}
+        for m, x in (("ap", batch["spikes_data"]), ("behavior", batch["target"])):
+            if mode == "token_masking":
+                mk = torch.bernoulli(torch.full((B, 100), 0.3), generator=g).long()
+            else:
+                mk = torch.full((B, 100), 1 if (m == "ap") == (mode == "encoding") else 0, dtype=torch.int64)
+            ob[m] = dict(inputs=x, targets=x, attn_mask=attn, timestamp=batch["spikes_timestamps"], mask=mk & attn)
+        t0 = time.perf_counter()
+        # dropout_seed set: train() mode like the GPU arm (masks from the documented Philox stream)
+        orc.forward_backward(P, spec, ob, dropout_seed=None if a.eval_mode else 1000 + step)
+        return time.perf_counter() - t0
+
+    for s in range(warmup):
+        one(s)
+    times = []
+    t_start = time.perf_counter()
+    s = warmup
+    while True:
+        times.append(one(s))
+        s += 1
+        if fixed_steps and len(times) >= fixed_steps:
+            break
+        if not fixed_steps and len(times) >= min_steps and time.perf_counter() - t_start >= seconds:
+            break
+    per = sum(times) / len(times)
+    return B / per, cores, len(times), per
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, a.steps)
+    # bounded: each step = one fwd+bwd over a 16-trial sample of the workload
+    rate, cores, n, per = cpu_reference_rate(a, 0.0, fixed_steps=min(steps, 12), warmup=min(max(a.warmup, 1), 2))
+    cfg = workload_config(a, a.gpus)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
+        "warmup": min(max(a.warmup, 1), 2), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} fwd+bwd steps of {a.cpu_batch} trials each (same model / N / T as the "
+                                   f"GPU arm), oracle/mm_oracle.py, torch fp32, {cores} threads"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from multi_modal_foundation_model_b200 import ops
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch, make_mod_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    cfg = default_model_config()
+    torch.manual_seed(42)
+    model = build_model(a.neurons, 2, cfg).to(dev)
+    model.train(not a.eval_mode)
+    model.masker.stream = "fast"     # throughput mode: draw only the (B,T) field the model uses (masker.py docstring)
+    eng = model.engine()
+    ddp = None
+    if world > 1:
+        from multi_modal_foundation_model_b200.parallel import DataParallel
+        ddp = DataParallel(model)
+    B = a.batch
+
+    # rank r's shard of every global batch: its own seeded trials (weak scaling: B per GPU)
+    host_batches = [make_batch(B, a.neurons, 2, 100, step=1000 * rank + i, pin=True) for i in range(3)]
+    dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
+    dev_dicts = [make_mod_dict(dev_batches[i], ["ap", "behavior"], MODES[i], device=dev) for i in range(3)]
+
+    def step_resident(i):
+        md = {k: dict(v) for k, v in dev_dicts[i % 3].items()}
+        out = model(md)
+        out.loss.backward()
+        model.zero_grad(set_to_none=True)
+        return out
+
+    def step_e2e(i):
+        hb = host_batches[i % 3]
+        db = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}   # H2D
+        md = make_mod_dict(db, ["ap", "behavior"], MODES[i % 3], device=dev)
+        out = model(md)
+        out.loss.backward()
+        model.zero_grad(set_to_none=True)
+        return float(out.loss.item())                                                                  # D2H
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * n_gpus * a.steps / (ms / 1e3)
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, a.steps)
+    e2e_value = B * n_gpus * a.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values() if torch.is_tensor(v))
+
+    pl = eng.last_plan
+    launches = (ops.count_kernels(pl.fwd_calls) + ops.count_kernels(pl.bwd_calls)) * a.steps
+
+    # ---- per-kernel timing (events around every launch, separate pass) -> roofline of the dominant kernel ----
+    roofline = None
+    kernel_table = {}
+    if rank == 0:
+        agg = {}
+        reps = 3
+        for _ in range(reps):
+            pl.seed.add_(1)
+            for name, meta, t in ops.run_recorded_timed(pl.fwd_calls) + ops.run_recorded_timed(pl.bwd_calls):
+                d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
+                d["ms"] += t
+                d["n"] += 1
+                d["flops"] += meta.get("flops", 0.0)
+                d["bytes"] += meta.get("bytes", 0.0)
+        total = sum(d["ms"] for d in agg.values())
+        for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            kernel_table[name] = {"ms_per_step": round(d["ms"] / reps, 4), "launches_per_step": d["n"] // reps,
+                                  "share": round(d["ms"] / total, 4),
+                                  "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2) if d["flops"] else None,
+                                  "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        top = next(iter(kernel_table))
+        d = agg[top]
+        if d["flops"]:
+            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF"}
+        else:
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+        rate, cores, n, per = cpu_reference_rate(a, a.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} fwd+bwd steps of {a.cpu_batch} trials (same model / N / T), oracle/mm_oracle.py, torch "
+                         f"fp32, {cores} threads, {per:.2f} s/step"}
+
+    if rank == 0:
+        cfgj = workload_config(a, n_gpus)
+        cfgj["l2_policy"] = "per-step working set (activations + saved tensors, several GB at B=256) >> 126 MB L2"
+        flops_step = 3 * 3.79e9 * B if a.neurons == 668 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfgj, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
+            "step_tensor_frac": (flops_step / (ms / a.steps * 1e-3) / 1e12 / 1370.0) if flops_step else None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

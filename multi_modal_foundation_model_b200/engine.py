@@ -485,6 +485,12 @@ class Plan:
         du = b16(R, max(eng.enc_inter, eng.dec_inter))
         self.delta = f32(B, max(hp["enc_heads"], hp["dec_heads"]), S)
         ddec = b16(R, H)                                       # gradient wrt decoder_norm output (modality-major)
+        self.grad_marks: List[Tuple[int, int]] = []           # (calls issued, flat-gradient offset that is final)
+
+        def mark(next_param: Optional[str]):
+            rec = ops._REC
+            off = st.total if next_param is None else st.offset[st.alias[next_param]]
+            self.grad_marks.append((len(rec.calls), off))
 
         def lin_bwd(dY, X, wname, shadow_key, dX, *, act=ACT_NONE, aux=None, act_scale=1.0, wnames=None, bnames=None):
             """dX = dY . W ; dW += dY^T X ; db += colsum(dY)"""
@@ -547,6 +553,7 @@ class Plan:
             prev = self._drop(SITE_MLP, i - 1, SIDE_DEC, hp["dec_dropout"]) if i > 0 else NO_DROP
             attn_bwd(pre + ".attn", y0, pre + ".ln1", G, dec_mode, hp["dec_heads"], hp["dec_dropout"], i, SIDE_DEC,
                      eng.sep, Gb if i > 0 else None, prev)
+            mark(f"decoder.{i - 1}.mlp.down_proj.weight" if i > 0 else "decoder_proj_context.weight")
 
         # ---- context projection + encoder ------------------------------------------------------------------
         lin_bwd(Gcb, A["encoder_norm"], "decoder_proj_context", "decoder_proj_context", dh)
@@ -558,6 +565,8 @@ class Plan:
             prev = self._drop(SITE_MLP, i - 1, SIDE_ENC, hp["enc_dropout"]) if i > 0 else NO_DROP
             attn_bwd(pre + ".attn", self.xs[2 * i], pre + ".ln1", Genc, MASK_KEY_OR_DIAG, hp["enc_heads"],
                      hp["enc_dropout"], i, SIDE_ENC, False, Gb if i > 0 else None, prev)
+            if i > 0:
+                mark(f"encoder.{i - 1}.mlp.down_proj.weight")
 
         # ---- embeddings ------------------------------------------------------------------------------------
         dtok = b16(BT, H)
@@ -584,6 +593,7 @@ class Plan:
                     lin_bwd(dtok, A[pre + ".hid"], pre + ".projection", pre + ".projection", dhid, act=back,
                             aux=A[pre + ".hid"] if back else None, act_scale=eng.embed_scale)
                     lin_bwd(dhid, self.inb[m.name], pre + ".token_embed", None, None)
+        mark(None)
         ops.scale_inplace(st.grad, self.gscale)
 
     # ---------------------------------------------------------------------------------------------------

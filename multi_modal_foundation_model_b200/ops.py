@@ -55,8 +55,8 @@ class Recorder:
         self.calls: List[Tuple[Callable, tuple, str]] = []
         self.keep: List[object] = []   # ctypes structs must outlive the recorded calls
 
-    def add(self, fn, args, what):
-        self.calls.append((fn, args, what))
+    def add(self, fn, args, what, meta=None):
+        self.calls.append((fn, args, what, meta or {}))
 
 
 _REC: Optional[Recorder] = None
@@ -67,21 +67,46 @@ def set_recorder(r: Optional[Recorder]) -> None:
     _REC = r
 
 
-def _launch(name: str, *args, keep=()):
+def _launch(name: str, *args, keep=(), meta=None):
     fn = getattr(lib(), name)
     if _REC is not None:
         _REC.keep.extend(keep)
-        _REC.add(fn, args, name)
+        _REC.add(fn, args, name, meta)
         return
     check(fn(*args, _stream()), name)
 
 
-def run_recorded(calls: Sequence[Tuple[Callable, tuple, str]]) -> None:
+def run_recorded(calls) -> None:
     st = _stream()
-    for fn, args, what in calls:
-        rc = fn(*args, st)
+    for c in calls:
+        rc = c[0](*c[1], st)
         if rc != 0:
-            check(rc, what)
+            check(rc, c[2])
+
+
+# kernels launched per C call (mmfm_attention_bwd = prep + dq + dkv)
+KERNELS_PER_CALL = {"mmfm_attention_bwd": 3}
+
+
+def count_kernels(calls) -> int:
+    return sum(KERNELS_PER_CALL.get(c[2], 1) for c in calls)
+
+
+def run_recorded_timed(calls):
+    """One pass with a CUDA-event pair around every call; returns [(name, meta, ms)] (profiling aid for bench.py:
+    events on the launching stream, never used for the headline number)."""
+    st = _stream()
+    evs = []
+    for c in calls:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = c[0](*c[1], st)
+        e1.record()
+        if rc != 0:
+            check(rc, c[2])
+        evs.append((c[2], c[3], e0, e1))
+    torch.cuda.synchronize()
+    return [(n, m, e0.elapsed_time(e1)) for n, m, e0, e1 in evs]
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -113,7 +138,7 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, M: Optional[in
     a.drop = drop.c()
     a.remap_T, a.remap_S, a.remap_off = remap
     a.row_zero = _p(row_zero)
-    _launch("mmfm_gemm_tn", C.byref(a), keep=(a,))
+    _launch("mmfm_gemm_tn", C.byref(a), keep=(a,), meta={"flops": 2.0 * a.M * a.N * a.K, "tag": f"gemm_tn {a.M}x{a.N}x{a.K}"})
 
 
 def gemm_wgrad(dY: torch.Tensor, X: torch.Tensor, dW: torch.Tensor, *, R: Optional[int] = None,
@@ -124,7 +149,7 @@ def gemm_wgrad(dY: torch.Tensor, X: torch.Tensor, dW: torch.Tensor, *, R: Option
     NO = NO if NO is not None else dY.shape[1]
     KI = KI if KI is not None else X.shape[1]
     _launch("mmfm_gemm_wgrad", dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), R, NO, KI, dW.data_ptr(),
-            ldw if ldw is not None else KI)
+            ldw if ldw is not None else KI, meta={"flops": 2.0 * R * NO * KI, "tag": f"wgrad {R}x{NO}x{KI}"})
 
 
 def colsum_bf16(dY: torch.Tensor, out: torch.Tensor, *, R: Optional[int] = None, NO: Optional[int] = None) -> None:
@@ -152,14 +177,16 @@ def scale_inplace(x: torch.Tensor, scale_dev: torch.Tensor) -> None:
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, *, R: int, H: int, eps: float = 1e-5, modmajor_T: int = 0,
                   S: int = 0) -> None:
     _launch("mmfm_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-            rstd.data_ptr(), R, H, eps, modmajor_T, S)
+            rstd.data_ptr(), R, H, eps, modmajor_T, S, meta={"bytes": 6.0 * R * H})
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dxb, drop: DropSpec, dgamma, dbeta, *, R: int, H: int,
                   modmajor_T: int = 0, S: int = 0) -> None:
     d = drop.c()
     _launch("mmfm_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-            _p(dres), _p(dx), _p(dxb), C.byref(d), _p(dgamma), _p(dbeta), R, H, modmajor_T, S, keep=(d,))
+            _p(dres), _p(dx), _p(dxb), C.byref(d), _p(dgamma), _p(dbeta), R, H, modmajor_T, S, keep=(d,),
+            meta={"bytes": float(R) * H * (2 + 4 + (4 if dres is not None else 0) + (4 if dx is not None else 0)
+                                           + (2 if dxb is not None else 0))})
 
 
 def _attn_args(q, k, v, o, lse, key_valid, *, B, n_heads, Sq, Sk, d_head, mask_mode, mod_q=None, mod_k=None,
@@ -190,12 +217,14 @@ def _attn_args(q, k, v, o, lse, key_valid, *, B, n_heads, Sq, Sk, d_head, mask_m
 def attention_fwd(q, k, v, o, lse, key_valid, **kw) -> None:
     """q/k/v/o: 2-D bf16 views [B*S, h*d] (row pitch = stride(0)); see include/mmfm_b200.h."""
     a = _attn_args(q, k, v, o, lse, key_valid, **kw)
-    _launch("mmfm_attention_fwd", C.byref(a), keep=(a,))
+    _launch("mmfm_attention_fwd", C.byref(a), keep=(a,),
+            meta={"flops": 4.0 * a.B * a.n_heads * a.Sq * a.Sk * a.d_head})
 
 
 def attention_bwd(q, k, v, o, lse, key_valid, **kw) -> None:
     a = _attn_args(q, k, v, o, lse, key_valid, **kw)
-    _launch("mmfm_attention_bwd", C.byref(a), keep=(a,))
+    _launch("mmfm_attention_bwd", C.byref(a), keep=(a,),
+            meta={"flops": 8.0 * a.B * a.n_heads * a.Sq * a.Sk * a.d_head})   # algorithmic: 2x forward
 
 
 def mask_prep(masks: Sequence[Optional[torch.Tensor]], attns: Sequence[torch.Tensor], channels: Sequence[int],
@@ -257,7 +286,8 @@ def smallc_head_bwd(y, W, dpreds, dy, dW, db, *, R, H, Cc) -> None:
 
 def loss_fwd_bwd(preds, targets, tok_mask, inv_n, kind, partials, dpreds, *, B, T, Cc, S, off) -> None:
     _launch("mmfm_loss_fwd_bwd", preds.data_ptr(), targets.data_ptr(), tok_mask.data_ptr(), S, off, inv_n.data_ptr(),
-            kind, B, T, Cc, partials.data_ptr(), partials.numel(), dpreds.data_ptr(), dpreds.stride(0))
+            kind, B, T, Cc, partials.data_ptr(), partials.numel(), dpreds.data_ptr(), dpreds.stride(0),
+            meta={"bytes": 10.0 * B * T * Cc})
 
 
 def loss_finalize(partials, n_partials, n_mod, inv_n, mod_loss, loss) -> None:
