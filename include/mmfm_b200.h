@@ -75,10 +75,11 @@ typedef struct mmfm_gemm_args {
  * encoder_embeddings.py:50,54; decoder_embeddings.py:50,54,107; mm.py:292) and its autograd dgrad. */
 int mmfm_gemm_tn(const mmfm_gemm_args* args, void* stream);
 
-/* dW[NO,KI] += dY[R,NO]^T . X[R,KI]  (fp32 accumulate with red.global.add; caller zeroes dW once per step).
- * Replaces the autograd wgrad of every nn.Linear on the path. */
+/* dW[NO,KI] += dY[R,NO]^T . X[R,KI]  (fp32 accumulate with red.global.add; caller zeroes dW once per step);
+ * dbias (optional, [NO]) += column sums of dY, computed on the tensor pipe in the same pass.
+ * Replaces the autograd wgrad (weight and bias) of every nn.Linear on the path. */
 int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI, float* dW,
-                    long long ldw, void* stream);
+                    long long ldw, float* dbias, void* stream);
 /* out[c] += sum_r dY[r,c]  (bias gradient) */
 int mmfm_colsum_bf16(const void* dY, long long ld, int R, int NO, float* out, void* stream);
 

@@ -140,7 +140,7 @@ _DP = C.POINTER(Dropout)
 # name -> argtypes; every function returns int except the three listed in _SPECIAL
 SIGNATURES = {
     "mmfm_gemm_tn": [C.POINTER(GemmArgs), _vp],
-    "mmfm_gemm_wgrad": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _vp],
+    "mmfm_gemm_wgrad": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _vp, _vp],
     "mmfm_colsum_bf16": [_vp, _ll, _i, _i, _vp, _vp],
     "mmfm_cast_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp],
     "mmfm_cast_bf16_multi": [_vp, _i, _i, _vp],

@@ -21,145 +21,93 @@ constexpr int kBK = 64;
 constexpr int kGemmThreads = 192;
 
 // ------------------------------------------------------------------------------------------------
-// epilogue math on 16 consecutive columns of one row
+// Epilogue, two phases per epilogue warp (each warp owns the 32 accumulator rows of its TMEM lane quadrant):
+//   A  thread = row : tcgen05.ld 32 columns at a time, + bias (smem broadcast), dropout (the thread holds whole
+//      16-column Philox groups of its row), token zeroing -> fp32 staging tile in shared memory (the drained
+//      pipeline stages are reused)
+//   B  lane = 4 consecutive columns, one row (BN = 128) or two rows (BN = 64) per step: activation / saved-tensor
+//      derivative, residual add, 16-byte coalesced global loads and stores (a warp touches one contiguous 512-byte
+//      row segment per instruction instead of 32 rows x 16 bytes)
+// Only __syncwarp separates the phases: a warp re-reads exactly the rows it staged.
 // ------------------------------------------------------------------------------------------------
-struct EpiRow {
-  bool valid;         // row < M
-  bool zero;          // token zeroing flag
-  long long out_row;  // output row after remap
-  long long row;      // GEMM row (dropout field row, aux row)
+MMFM_DEVINL float4 ld4_f32(const float* p, bool vec, int nvalid) {
+  if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) r.x = __ldg(p);
+  if (nvalid > 1) r.y = __ldg(p + 1);
+  if (nvalid > 2) r.z = __ldg(p + 2);
+  if (nvalid > 3) r.w = __ldg(p + 3);
+  return r;
+}
+MMFM_DEVINL float4 ld4_bf16(const bf16* p, bool vec, int nvalid) {
+  if (vec) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid > 0) r.x = __bfloat162float(p[0]);
+  if (nvalid > 1) r.y = __bfloat162float(p[1]);
+  if (nvalid > 2) r.z = __bfloat162float(p[2]);
+  if (nvalid > 3) r.w = __bfloat162float(p[3]);
+  return r;
+}
+MMFM_DEVINL void st4_f32(float* p, bool vec, int nvalid, const float4& v) {
+  if (vec) { *reinterpret_cast<float4*>(p) = v; return; }
+  if (nvalid > 0) p[0] = v.x;
+  if (nvalid > 1) p[1] = v.y;
+  if (nvalid > 2) p[2] = v.z;
+  if (nvalid > 3) p[3] = v.w;
+}
+MMFM_DEVINL void st4_bf16(bf16* p, bool vec, int nvalid, const float4& v) {
+  if (vec) { *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)); return; }
+  if (nvalid > 0) p[0] = __float2bfloat16_rn(v.x);
+  if (nvalid > 1) p[1] = __float2bfloat16_rn(v.y);
+  if (nvalid > 2) p[2] = __float2bfloat16_rn(v.z);
+  if (nvalid > 3) p[3] = __float2bfloat16_rn(v.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TN kernel.  Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per TMEM
+// lane quadrant, each taking one half of the tile's columns).  The epilogue flavour is a template parameter so the
+// per-element code is branch-free; EPI_GENERIC keeps every run-time option (unaligned pitches, odd N).
+// ------------------------------------------------------------------------------------------------
+constexpr int kEpiWarps = 8;
+constexpr int kTnThreads = 64 + kEpiWarps * 32;
+
+enum EpiKind : int {
+  EPI_PLAIN_BF16 = 0,   // D(bf16) = v
+  EPI_PLAIN_F32 = 1,    // D(f32) = v
+  EPI_RES_F32 = 2,      // D(f32) = v + res                       (dropout / token zeroing / remap allowed)
+  EPI_GELU = 3,         // D2(bf16) = v ; D(bf16) = gelu(v)
+  EPI_SOFTSIGN = 4,     // D(bf16) = softsign(v) * s
+  EPI_DGELU = 5,        // D(bf16) = v * gelu'(aux)
+  EPI_DSOFTSIGN = 6,    // D(bf16) = v * s * (1 - |aux/s|)^2
+  EPI_GENERIC = 7
 };
 
-MMFM_DEVINL void load16_f32(const float* p, bool vec, int nvalid, float (&o)[16]) {
-  if (vec && nvalid == 16) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
-      o[4 * j] = t.x; o[4 * j + 1] = t.y; o[4 * j + 2] = t.z; o[4 * j + 3] = t.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = (j < nvalid) ? __ldg(p + j) : 0.f;
-  }
-}
-MMFM_DEVINL void load16_bf16(const bf16* p, bool vec, int nvalid, float (&o)[16]) {
-  if (vec && nvalid == 16) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + j);
-      float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-      o[8 * j] = a.x; o[8 * j + 1] = a.y; o[8 * j + 2] = b.x; o[8 * j + 3] = b.y;
-      o[8 * j + 4] = c.x; o[8 * j + 5] = c.y; o[8 * j + 6] = d.x; o[8 * j + 7] = d.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = (j < nvalid) ? __bfloat162float(p[j]) : 0.f;
-  }
-}
-MMFM_DEVINL void store16_f32(float* p, bool vec, int nvalid, const float (&v)[16]) {
-  if (vec && nvalid == 16) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < nvalid) p[j] = v[j];
-  }
-}
-MMFM_DEVINL void store16_bf16(bf16* p, bool vec, int nvalid, const float (&v)[16]) {
-  if (vec && nvalid == 16) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      reinterpret_cast<uint4*>(p)[j] =
-          make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < nvalid) p[j] = __float2bfloat16_rn(v[j]);
-  }
-}
-
-MMFM_DEVINL void epilogue16(const mmfm_gemm_args& p, const EpiRow& er, int n, float (&v)[16], unsigned long long seed,
-                            uint32_t drop_gpr) {
-  const int nvalid = min(16, p.N - n);
-  if (p.bias) {
-    float b[16];
-    load16_f32(p.bias + n, (reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0, nvalid, b);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += b[j];
-  }
-  if (p.act == MMFM_ACT_GELU) {
-    if (p.D2) {
-      bf16* d2 = reinterpret_cast<bf16*>(p.D2) + er.out_row * p.ldd + n;
-      store16_bf16(d2, (reinterpret_cast<uintptr_t>(d2) & 15) == 0, nvalid, v);
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == MMFM_ACT_SOFTSIGN) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = softsign(v[j]) * p.act_scale;
-  } else if (p.act == MMFM_ACT_DGELU || p.act == MMFM_ACT_DSOFTSIGN) {
-    float a[16];
-    const bf16* ap = reinterpret_cast<const bf16*>(p.aux) + er.row * p.ldaux + n;
-    load16_bf16(ap, (reinterpret_cast<uintptr_t>(ap) & 15) == 0, nvalid, a);
-    if (p.act == MMFM_ACT_DGELU) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(a[j]);
-    } else {
-      const float inv = 1.0f / p.act_scale;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float t = 1.0f - fabsf(a[j] * inv);
-        v[j] *= p.act_scale * t * t;
-      }
-    }
-  }
-  if (p.drop.thresh != 0u) {
-    uint4 w = drop_bytes16(seed, p.drop.site, (uint64_t)er.row, drop_gpr, (uint32_t)(n >> 4));
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (drop_byte(w, j) < p.drop.thresh) ? 0.f : v[j] * p.drop.scale;
-  }
-  if (er.zero) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-  }
-  if (p.res) {
-    float r[16];
-    const float* rp = p.res + er.out_row * p.ldr + n;
-    load16_f32(rp, (reinterpret_cast<uintptr_t>(rp) & 15) == 0, nvalid, r);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += r[j];
-  }
-  if (p.d_fp32) {
-    float* dp = reinterpret_cast<float*>(p.D) + er.out_row * p.ldd + n;
-    store16_f32(dp, (reinterpret_cast<uintptr_t>(dp) & 15) == 0, nvalid, v);
-  } else {
-    bf16* dp = reinterpret_cast<bf16*>(p.D) + er.out_row * p.ldd + n;
-    store16_bf16(dp, (reinterpret_cast<uintptr_t>(dp) & 15) == 0, nvalid, v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// TN kernel
-// ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                const mmfm_gemm_args p) {
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(kTnThreads, 2) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const mmfm_gemm_args p) {
   constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
   constexpr uint32_t kBBytes = BN * kBK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr int kPitch = BN + 4;  // fp32 staging pitch (floats): 16-byte rows, conflict-free in both phases
+  constexpr int kHalf = BN / 2;   // columns per epilogue warp
+  static_assert((size_t)kBM * kPitch * 4 <= (size_t)STAGES * kStageBytes, "staging tile must fit in the stages");
+  constexpr bool GEN = EPI == EPI_GENERIC;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[BN];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  float* stage_f = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -180,6 +128,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
   if (warp == 1) {
     tmem_alloc(&tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int c = threadIdx.x - 64; c < BN; c += kEpiWarps * 32)
+      s_bias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -217,46 +169,150 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
       umma_commit(&accum_bar);
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrants (warp % 4)
+    // ---------------- epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------
     const int quad = warp & 3;
-    const long long r = (long long)m0 + quad * 32 + lane;
-    EpiRow er;
-    er.valid = r < p.M;
-    er.row = r;
-    er.out_row = r;
-    er.zero = false;
-    if (er.valid) {
-      if (p.remap_T > 0) {
-        const long long b = r / p.remap_T;
-        const int t = (int)(r - b * p.remap_T);
-        er.out_row = b * p.remap_S + p.remap_off + t;
-        if (p.row_zero) er.zero = p.row_zero[p.remap_off + t] != 0;
-      } else if (p.row_zero) {
-        er.zero = p.row_zero[(int)(r % p.remap_S)] != 0;
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * kHalf;
+    const int row_l = quad * 32 + lane;            // tile row of this thread (phase A)
+    const long long r = (long long)m0 + row_l;     // GEMM row
+    constexpr bool kMayDrop = GEN || EPI == EPI_RES_F32;
+    constexpr bool kHasRes = GEN || EPI == EPI_RES_F32;
+    constexpr bool kHasAux = GEN || EPI == EPI_DGELU || EPI == EPI_DSOFTSIGN;
+    bool zero = false;
+    bool drop = false;
+    unsigned long long seed = 0ull;
+    if (kMayDrop) {
+      if (p.row_zero && r < p.M) {
+        const int pos = p.remap_T > 0 ? p.remap_off + (int)(r % p.remap_T) : (int)(r % p.remap_S);
+        zero = p.row_zero[pos] != 0;
+      }
+      drop = p.drop.thresh != 0u;
+      if (drop) seed = *p.drop.seed;
+    }
+    const uint32_t drop_gpr = (uint32_t)((p.N + 15) >> 4);
+    const bool warp_has_cols = (n0 + cbase) < p.N;
+
+    // while the main loop runs: pull this thread's residual / saved-tensor row segment into L2
+    if (r < p.M && warp_has_cols) {
+      const int ncols = min(kHalf, p.N - n0 - cbase);
+      if (kHasRes && p.res) {
+        long long orow = r;
+        if (p.remap_T > 0) {
+          const int bb = (int)r / p.remap_T;
+          orow = (long long)bb * p.remap_S + p.remap_off + ((int)r - bb * p.remap_T);
+        }
+        const char* ptr = reinterpret_cast<const char*>(p.res + orow * p.ldr + n0 + cbase);
+        for (int o = 0; o < ncols * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
+      }
+      if (kHasAux && p.aux) {
+        const char* ptr =
+            reinterpret_cast<const char*>(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + n0 + cbase);
+        for (int o = 0; o < ncols * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
       }
     }
-    unsigned long long seed = 0ull;
-    if (p.drop.thresh != 0u) seed = *p.drop.seed;
-    const uint32_t drop_gpr = (uint32_t)((p.N + 15) >> 4);
-
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if (warp_has_cols) {
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase;
+      float* my_row = stage_f + row_l * kPitch + cbase;
+      // ---------------- phase A: thread = row ----------------
+#pragma unroll
+      for (int c0 = 0; c0 < kHalf; c0 += 16) {
+        uint32_t acc[16];
+        tmem_ld16(t_row + (uint32_t)c0, acc);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + j4 * 4]);
+          v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b4.x;
+          v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b4.y;
+          v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b4.z;
+          v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b4.w;
+        }
+        if (kMayDrop) {
+          if (drop) {
+            const uint4 w = drop_bytes16(seed, p.drop.site, (uint64_t)r, drop_gpr, (uint32_t)((n0 + cbase + c0) >> 4));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = (drop_byte(w, j) < p.drop.thresh) ? 0.f : v[j] * p.drop.scale;
+          }
+          if (zero) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          *reinterpret_cast<float4*>(my_row + c0 + j4 * 4) =
+              make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      }
+      __syncwarp();
+      // ---------------- phase B: lane = 4 consecutive columns; coalesced global traffic ----------------
+      constexpr int kLanesPerRow = kHalf / 4;          // 16 (BN 128) or 8 (BN 64)
+      constexpr int kRowsPerStep = 32 / kLanesPerRow;  // 2 or 4
+      constexpr int kSteps = 32 / kRowsPerStep;        // 16 or 8
+      constexpr int kBatch = 8;                        // steps whose global loads are issued together
+      const int lcol = cbase + (lane % kLanesPerRow) * 4;
+      const int n = n0 + lcol;
+      const int nvalid = p.N - n;
+      const int lrow = lane / kLanesPerRow;
+      const int act = GEN ? p.act : 0;
+      const bool f32out = GEN ? (p.d_fp32 != 0) : (EPI == EPI_PLAIN_F32 || EPI == EPI_RES_F32);
+      // the specialised kernels are only launched when every pointer / pitch is vector-aligned and N % 4 == 0
+      const bool vec_d = GEN ? ((p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D) & (p.d_fp32 ? 15 : 7)) == 0)) : true;
+      const bool vec_d2 = GEN ? (p.D2 && (p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D2) & 7) == 0)) : true;
+      const bool vec_r = GEN ? (p.res && (p.ldr % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)) : true;
+      const bool vec_a = GEN ? (p.aux && (p.ldaux % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0)) : true;
+      const float inv_scale = 1.0f / p.act_scale;
+      const bool has_res = GEN ? (p.res != nullptr) : (EPI == EPI_RES_F32);
+      const bool has_aux = GEN ? (act == MMFM_ACT_DGELU || act == MMFM_ACT_DSOFTSIGN) : kHasAux;
+      if (nvalid > 0) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;  // warp-uniform
-      uint32_t acc[32];
-      tmem_ld32(t_row + (uint32_t)c0, acc);
-      tmem_ld_wait();
-      if (er.valid) {
+        for (int it0 = 0; it0 < kSteps; it0 += kBatch) {
+          float4 rv[kBatch], av[kBatch];
+          long long orow[kBatch];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n = n0 + c0 + g * 16;
-          if (n < p.N) {
-            float v[16];
+          for (int u = 0; u < kBatch; ++u) {
+            const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
+            const long long rr = (long long)m0 + rl;
+            orow[u] = rr;
+            if (kMayDrop && p.remap_T > 0) {
+              const int bb = (int)rr / p.remap_T;
+              orow[u] = (long long)bb * p.remap_S + p.remap_off + ((int)rr - bb * p.remap_T);
+            }
+            if (rr >= p.M) orow[u] = -1;
+            rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            av[u] = rv[u];
+            if (orow[u] >= 0) {
+              if (has_res) rv[u] = ld4_f32(p.res + orow[u] * p.ldr + n, vec_r, nvalid);
+              if (has_aux) av[u] = ld4_bf16(reinterpret_cast<const bf16*>(p.aux) + rr * p.ldaux + n, vec_a, nvalid);
+            }
+          }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[g * 16 + j]);
-            epilogue16(p, er, n, v, seed, drop_gpr);
+          for (int u = 0; u < kBatch; ++u) {
+            if (orow[u] < 0) continue;
+            const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
+            float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
+            if (EPI == EPI_GELU || (GEN && act == MMFM_ACT_GELU)) {
+              if (!GEN || p.D2) st4_bf16(reinterpret_cast<bf16*>(p.D2) + orow[u] * p.ldd + n, vec_d2, nvalid, v);
+              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            } else if (EPI == EPI_SOFTSIGN || (GEN && act == MMFM_ACT_SOFTSIGN)) {
+              v.x = softsign(v.x) * p.act_scale; v.y = softsign(v.y) * p.act_scale;
+              v.z = softsign(v.z) * p.act_scale; v.w = softsign(v.w) * p.act_scale;
+            } else if (EPI == EPI_DGELU || (GEN && act == MMFM_ACT_DGELU)) {
+              const float4 a = av[u];
+              v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(a.z); v.w *= gelu_erf_grad(a.w);
+            } else if (EPI == EPI_DSOFTSIGN || (GEN && act == MMFM_ACT_DSOFTSIGN)) {
+              const float4 a = av[u];
+              float t;
+              t = 1.0f - fabsf(a.x * inv_scale); v.x *= p.act_scale * t * t;
+              t = 1.0f - fabsf(a.y * inv_scale); v.y *= p.act_scale * t * t;
+              t = 1.0f - fabsf(a.z * inv_scale); v.z *= p.act_scale * t * t;
+              t = 1.0f - fabsf(a.w * inv_scale); v.w *= p.act_scale * t * t;
+            }
+            if (has_res) { v.x += rv[u].x; v.y += rv[u].y; v.z += rv[u].z; v.w += rv[u].w; }
+            if (f32out) st4_f32(reinterpret_cast<float*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
+            else st4_bf16(reinterpret_cast<bf16*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
           }
         }
       }
@@ -268,19 +324,24 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tn_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// wgrad kernel: dW[NO,KI] += sum over a slice of rows of dY[r,NO]^T X[r,KI]
+// wgrad kernel: dW[NO,KI] += sum over a slice of rows of dY[r,NO]^T X[r,KI];  optionally db[NO] += colsum(dY)
+// (the bias gradient rides on the tensor pipe: one extra N=16 MMA per k-step against a tile of ones)
 // ------------------------------------------------------------------------------------------------
 template <int STAGES>
 __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                    const __grid_constant__ CUtensorMap tmX, int R,
                                                                    int NO, int KI, float* __restrict__ dW,
-                                                                   long long ldw, int rows_per_split) {
+                                                                   long long ldw, int rows_per_split,
+                                                                   float* __restrict__ dbias) {
   constexpr int BN = 128;
   constexpr uint32_t kBoxBytes = 64 * kBK * 2;  // [64 rows(k) x 64 cols(mn)] bf16 = 8 KB
   constexpr uint32_t kABytes = 2 * kBoxBytes;
   constexpr uint32_t kBBytes = 2 * kBoxBytes;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BN;
+  constexpr uint32_t kOnesBytes = 2048;         // 16 k-rows x 128 B of bf16(1.0)
+  constexpr uint32_t kTmemCols = 256;           // 128 (dW tile) + 16 (bias column), power of two
+  constexpr int kPitch = BN + 4;
+  static_assert((size_t)kBM * kPitch * 4 <= (size_t)STAGES * kStageBytes, "staging tile must fit in the stages");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -289,6 +350,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* stage_f = reinterpret_cast<float*>(smem_al);
+  const uint32_t ones_addr = smem_base + STAGES * kStageBytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ki0 = blockIdx.x * BN;
@@ -296,6 +360,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   const int r_begin = blockIdx.z * rows_per_split;
   const int r_end = min(R, r_begin + rows_per_split);
   const int nkb = (r_end - r_begin + kBK - 1) / kBK;  // >= 1 by construction of the grid
+  const bool do_bias = (dbias != nullptr) && (blockIdx.x == 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
@@ -312,6 +377,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
     tmem_alloc(&tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (do_bias && warp >= 2) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_al + STAGES * kStageBytes);
+    for (int i = threadIdx.x - 64; i < (int)(kOnesBytes / 4); i += 128) ones[i] = 0x3F803F80u;
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -325,8 +395,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
         const uint32_t a_dst = smem_base + s * kStageBytes;
         const int r0 = r_begin + kb * kBK;
-        // NOTE: rows beyond r_end (but < R) of the last k-block belong to the next split; they are excluded by
-        // making rows_per_split a multiple of kBK on the host, so only the global tail (>= R) is zero-filled.
+        // rows_per_split is a multiple of kBK, so only the global tail (>= R) is zero-filled by TMA
         tma_load_2d_addr(a_dst, &tmY, &full_bar[s], no0, r0);
         tma_load_2d_addr(a_dst + kBoxBytes, &tmY, &full_bar[s], no0 + 64, r0);
         tma_load_2d_addr(a_dst + kABytes, &tmX, &full_bar[s], ki0, r0);
@@ -336,6 +405,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+      const uint32_t idesc_b = make_idesc_bf16(kBM, 16, 1, 1);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&full_bar[s], (kb / STAGES) & 1);
@@ -349,6 +419,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
           const uint64_t da = make_smem_desc(a_addr + k * 2048, kBoxBytes, 1024, 2);
           const uint64_t db = make_smem_desc(b_addr + k * 2048, kBoxBytes, 1024, 2);
           umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (do_bias) {
+            const uint64_t d1 = make_smem_desc(ones_addr, kBoxBytes, 1024, 2);
+            umma_bf16(tmem_base + BN, da, d1, idesc_b, (kb > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -356,21 +430,51 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
     }
   } else {
     const int quad = warp & 3;
-    const int no = no0 + quad * 32 + lane;
+    const int row_l = quad * 32 + lane;
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* my_row = stage_f + row_l * kPitch;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (ki0 + c0 >= KI) break;
       uint32_t acc[32];
       tmem_ld32(t_row + (uint32_t)c0, acc);
       tmem_ld_wait();
-      if (no < NO) {
-        float* dst = dW + (long long)no * ldw + ki0 + c0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (ki0 + c0 + j < KI) atomicAdd(dst + j, __uint_as_float(acc[j]));
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(my_row + c0 + j4 * 4) =
+            make_float4(__uint_as_float(acc[4 * j4]), __uint_as_float(acc[4 * j4 + 1]),
+                        __uint_as_float(acc[4 * j4 + 2]), __uint_as_float(acc[4 * j4 + 3]));
+    }
+    if (do_bias) {
+      uint32_t bacc[16];
+      tmem_ld16(t_row + (uint32_t)BN, bacc);
+      tmem_ld_wait();
+      if (no0 + row_l < NO) atomicAdd(dbias + no0 + row_l, __uint_as_float(bacc[0]));
+    }
+    __syncwarp();
+    // coalesced accumulation: lane = 4 consecutive columns, one row per step
+    const int lcol = lane * 4;
+    const int kcol = ki0 + lcol;
+    const int nvalid = KI - kcol;
+    const bool vec = (ldw % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+      const int rl = quad * 32 + it;
+      const int no = no0 + rl;
+      if (no >= NO || nvalid <= 0) continue;
+      const float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
+      float* dst = dW + (long long)no * ldw + kcol;
+      if (vec) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                     "f"(v.w)
+                     : "memory");
+      } else {
+        if (nvalid > 0) atomicAdd(dst, v.x);
+        if (nvalid > 1) atomicAdd(dst + 1, v.y);
+        if (nvalid > 2) atomicAdd(dst + 2, v.z);
+        if (nvalid > 3) atomicAdd(dst + 3, v.w);
       }
     }
   }
@@ -442,7 +546,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 using namespace mmfm;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI>
 static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_2d(&tmA, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, kBK, kBM, TMA_SW_128);
@@ -452,14 +556,45 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
     attr_set = true;
   }
   dim3 grid((a->N + BN - 1) / BN, (a->M + kBM - 1) / kBM, 1);
-  gemm_tn_kernel<BN, STAGES><<<grid, kGemmThreads, smem, st>>>(tmA, tmB, *a);
+  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int EPI>
+static int launch_tn_bn(const mmfm_gemm_args* a, cudaStream_t st) {
+  if (a->N <= 64) return launch_tn<64, 4, EPI>(a, st);
+  return launch_tn<128, 3, EPI>(a, st);
+}
+
+static bool al(const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; }
+
+// pick the branch-free epilogue when the call fits one of the flavours the model uses and everything is aligned
+static int pick_epi(const mmfm_gemm_args* a) {
+  if (a->N % 4 != 0 || a->ldd % 4 != 0) return EPI_GENERIC;
+  const bool f32 = a->d_fp32 != 0;
+  if (!al(a->D, f32 ? 16 : 8)) return EPI_GENERIC;
+  const bool extras = a->drop.thresh != 0 || a->row_zero != nullptr || a->remap_T > 0;
+  if (a->res) {
+    if (a->act != MMFM_ACT_NONE || !f32 || a->D2 || a->ldr % 4 != 0 || !al(a->res, 16)) return EPI_GENERIC;
+    return EPI_RES_F32;
+  }
+  if (extras) return EPI_GENERIC;
+  switch (a->act) {
+    case MMFM_ACT_NONE: return a->D2 ? EPI_GENERIC : (f32 ? EPI_PLAIN_F32 : EPI_PLAIN_BF16);
+    case MMFM_ACT_GELU: return (!f32 && a->D2 && al(a->D2, 8)) ? EPI_GELU : EPI_GENERIC;
+    case MMFM_ACT_SOFTSIGN: return (!f32 && !a->D2) ? EPI_SOFTSIGN : EPI_GENERIC;
+    case MMFM_ACT_DGELU:
+    case MMFM_ACT_DSOFTSIGN:
+      if (f32 || a->D2 || a->ldaux % 4 != 0 || !al(a->aux, 8)) return EPI_GENERIC;
+      return a->act == MMFM_ACT_DGELU ? EPI_DGELU : EPI_DSOFTSIGN;
+  }
+  return EPI_GENERIC;
 }
 
 extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
@@ -471,22 +606,32 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   MMFM_REQUIRE(a->drop.thresh == 0 || a->drop.seed, "mmfm_gemm_tn: dropout without seed pointer");
   MMFM_REQUIRE(a->drop.thresh < 256, "mmfm_gemm_tn: dropout threshold out of range");
   MMFM_REQUIRE(!(a->row_zero && a->remap_T == 0) || a->remap_S > 0, "mmfm_gemm_tn: row_zero needs remap_S");
+  MMFM_REQUIRE(a->act == MMFM_ACT_NONE || (a->drop.thresh == 0 && a->row_zero == nullptr),
+               "mmfm_gemm_tn: an activation epilogue cannot be combined with dropout / token zeroing");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->N <= 64) return launch_tn<64, 4>(a, st);
-  return launch_tn<128, 3>(a, st);
+  switch (pick_epi(a)) {
+    case EPI_PLAIN_BF16: return launch_tn_bn<EPI_PLAIN_BF16>(a, st);
+    case EPI_PLAIN_F32: return launch_tn_bn<EPI_PLAIN_F32>(a, st);
+    case EPI_RES_F32: return launch_tn_bn<EPI_RES_F32>(a, st);
+    case EPI_GELU: return launch_tn_bn<EPI_GELU>(a, st);
+    case EPI_SOFTSIGN: return launch_tn_bn<EPI_SOFTSIGN>(a, st);
+    case EPI_DGELU: return launch_tn_bn<EPI_DGELU>(a, st);
+    case EPI_DSOFTSIGN: return launch_tn_bn<EPI_DSOFTSIGN>(a, st);
+    default: return launch_tn_bn<EPI_GENERIC>(a, st);
+  }
 }
 
 extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI,
-                               float* dW, long long ldw, void* stream) {
+                               float* dW, long long ldw, float* dbias, void* stream) {
   MMFM_REQUIRE(dY && X && dW, "mmfm_gemm_wgrad: null operand");
   MMFM_REQUIRE(R > 0 && NO > 0 && KI > 0, "mmfm_gemm_wgrad: bad shape R=%d NO=%d KI=%d", R, NO, KI);
-  constexpr int STAGES = 4;
+  constexpr int STAGES = 3;
   CUtensorMap tmY, tmX;
   int rc = make_tmap_bf16_2d(&tmY, dY, (uint64_t)R, (uint64_t)NO, (uint64_t)lddy, 64, kBK, TMA_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmX, X, (uint64_t)R, (uint64_t)KI, (uint64_t)ldx, 64, kBK, TMA_SW_128);
   if (rc) return rc;
-  constexpr size_t smem = (size_t)STAGES * (4 * 64 * kBK * 2) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (4 * 64 * kBK * 2) + 2048 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -502,7 +647,7 @@ extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, lo
   splits = (R + rows_per_split - 1) / rows_per_split;
   dim3 grid((KI + 127) / 128, (NO + kBM - 1) / kBM, splits);
   gemm_wgrad_kernel<STAGES><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(tmY, tmX, R, NO, KI, dW, ldw,
-                                                                                 rows_per_split);
+                                                                                 rows_per_split, dbias);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

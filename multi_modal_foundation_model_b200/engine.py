@@ -274,6 +274,8 @@ class Plan:
             self._build_backward(f32, b16)
         finally:
             ops.set_recorder(None)
+        self._g_fwd = self._g_bwd = None
+        self._n_fwd_runs = self._n_bwd_runs = 0
         self.fwd_calls, self.bwd_calls = rec_f.calls, rec_b.calls
         self._keep += rec_f.keep + rec_b.keep
         self.n_fwd, self.n_bwd = len(self.fwd_calls), len(self.bwd_calls)
@@ -496,10 +498,9 @@ class Plan:
             """dX = dY . W ; dW += dY^T X ; db += colsum(dY)"""
             if dX is not None:
                 ops.gemm_tn(dY, sh.tr[shadow_key], dX, act=act, aux=aux, act_scale=act_scale)
-            ops.gemm_wgrad(dY, X, self._wgrad_dst(wnames or [wname + ".weight"]))
             bn = bnames or [wname + ".bias"]
-            if st.has(bn[0]):
-                ops.colsum_bf16(dY, self._bias(bn, "g"))
+            ops.gemm_wgrad(dY, X, self._wgrad_dst(wnames or [wname + ".weight"]),
+                           dbias=self._bias(bn, "g") if st.has(bn[0]) else None)
 
         def mlp_bwd(pre, x_in, ln_name, Gs, inter, dxb, drop_prev):
             duv = du[:, :inter]
@@ -597,13 +598,40 @@ class Plan:
         ops.scale_inplace(st.grad, self.gscale)
 
     # ---------------------------------------------------------------------------------------------------
-    def run_forward(self):
+    # -- execution: eager the first time (module load, kernel attributes), CUDA-graph replay afterwards ------
+    def _fwd_body(self):
         if self.training:
             self.seed.add_(0x632BE59BD9B4E019)
         ops.run_recorded(self.fwd_calls)
 
-    def run_backward(self):
+    def _bwd_body(self):
+        self.eng.store.grad.zero_()
         ops.run_recorded(self.bwd_calls)
+
+    def _capture(self, body):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        return g
+
+    def run_forward(self):
+        if self.eng.use_graphs and self._g_fwd is None and self._n_fwd_runs >= 1:
+            self._g_fwd = self._capture(self._fwd_body)
+        self._n_fwd_runs += 1
+        if self._g_fwd is not None:
+            self._g_fwd.replay()
+        else:
+            self._fwd_body()
+
+    def run_backward(self):
+        """Zeroes the flat gradient buffer and runs the backward schedule."""
+        if self.eng.use_graphs and self._g_bwd is None and self._n_bwd_runs >= 1:
+            self._g_bwd = self._capture(self._bwd_body)
+        self._n_bwd_runs += 1
+        if self._g_bwd is not None:
+            self._g_bwd.replay()
+        else:
+            self._bwd_body()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -662,7 +690,10 @@ class Engine:
         self.shadows = Shadows(self.store, model, self.mods)
         self.plans: Dict[Tuple[int, bool], Plan] = {}
         self.ddp = None          # set by parallel.DataParallel
+        import os as _os
+        self.use_graphs = _os.environ.get("MMFM_CUDA_GRAPHS", "1") != "0"
         self.last_plan: Optional[Plan] = None
+        self._grad_views = None
 
     # ---------------------------------------------------------------------------------------------------
     def _plan(self, B: int, T: int, training: bool) -> Plan:
@@ -743,9 +774,7 @@ class Engine:
         st = self.store
         fresh = all(p.grad is None for p in st.params.values())
         prev = None
-        if fresh:
-            st.grad.zero_()
-        else:
+        if not fresh:
             # gradient accumulation: keep what is there, compute this step into a clean buffer, then add
             if all(p.grad is None or p.grad.data_ptr() == st.g(n).data_ptr() for n, p in st.params.items()):
                 prev = st.grad.clone()
@@ -754,7 +783,6 @@ class Engine:
                 for n, p in st.params.items():
                     if p.grad is not None:
                         st.view(prev, n).copy_(p.grad)
-            st.grad.zero_()
         pl.gscale.copy_(grad_loss.reshape(1).to(torch.float32))
         if self.ddp is not None:
             self.ddp.run_backward(pl)
@@ -762,8 +790,9 @@ class Engine:
             pl.run_backward()
         if prev is not None:
             st.grad.add_(prev)
+        gv = self._grad_views
+        if gv is None:
+            gv = self._grad_views = {n: st.g(n) for n in st.params}
         for n, p in st.params.items():
-            if p.requires_grad:
-                g = st.g(n)
-                if p.grad is None or p.grad.data_ptr() != g.data_ptr():
-                    p.grad = g
+            if p.grad is not gv[n] and p.requires_grad:
+                p.grad = gv[n]

@@ -142,14 +142,16 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, M: Optional[in
 
 
 def gemm_wgrad(dY: torch.Tensor, X: torch.Tensor, dW: torch.Tensor, *, R: Optional[int] = None,
-               NO: Optional[int] = None, KI: Optional[int] = None, ldw: Optional[int] = None) -> None:
-    """dW[NO,KI] += dY[R,NO]^T . X[R,KI]"""
+               NO: Optional[int] = None, KI: Optional[int] = None, ldw: Optional[int] = None,
+               dbias: Optional[torch.Tensor] = None) -> None:
+    """dW[NO,KI] += dY[R,NO]^T . X[R,KI] ; dbias[NO] += colsum(dY) (optional)"""
     assert dY.dtype == bf16 and X.dtype == bf16 and dW.dtype == torch.float32
     R = R if R is not None else dY.shape[0]
     NO = NO if NO is not None else dY.shape[1]
     KI = KI if KI is not None else X.shape[1]
     _launch("mmfm_gemm_wgrad", dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), R, NO, KI, dW.data_ptr(),
-            ldw if ldw is not None else KI, meta={"flops": 2.0 * R * NO * KI, "tag": f"wgrad {R}x{NO}x{KI}"})
+            ldw if ldw is not None else KI, _p(dbias),
+            meta={"flops": 2.0 * R * NO * KI, "tag": f"wgrad {R}x{NO}x{KI}"})
 
 
 def colsum_bf16(dY: torch.Tensor, out: torch.Tensor, *, R: Optional[int] = None, NO: Optional[int] = None) -> None:

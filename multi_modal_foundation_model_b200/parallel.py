@@ -86,6 +86,7 @@ class DataParallel:
         from . import ops
         n_calls, buckets = self._segments(pl)
         grad = self.eng.store.grad
+        grad.zero_()
         works = []
         done = 0
         for ci, lo, hi in buckets:

@@ -105,9 +105,14 @@ def test_gemm_wgrad(R, NO, KI):
     from multi_modal_foundation_model_b200 import ops
     dY, X = _mk(R, NO, seed=9, scale=0.1), _mk(R, KI, seed=10)
     dW = torch.ones(NO, KI, device="cuda")
-    ops.gemm_wgrad(dY, X, dW, R=R, NO=NO, KI=KI)
+    db = torch.full((NO,), 2.0, device="cuda")
+    ops.gemm_wgrad(dY, X, dW, R=R, NO=NO, KI=KI, dbias=db)
     ref = dY.float().T @ X.float() + 1.0
     _close(dW, ref, 3e-3, f"wgrad {R}x{NO}x{KI}")
+    _close(db, dY.float().sum(0) + 2.0, 3e-3, f"wgrad bias {R}x{NO}")
+    dW2 = torch.zeros(NO, KI, device="cuda")
+    ops.gemm_wgrad(dY, X, dW2, R=R, NO=NO, KI=KI)           # without the bias column
+    _close(dW2, ref - 1.0, 3e-3, f"wgrad (no bias) {R}x{NO}x{KI}")
 
 
 def test_colsum_and_cast():

@@ -1,0 +1,57 @@
+"""Micro-benchmark of the GEMM epilogue variants on the shapes of the default model at B=256 (R = 51200 rows).
+CUDA events, L2 flushed between iterations by cycling through several copies of the operands."""
+import sys
+import torch
+sys.path.insert(0, '.')
+from multi_modal_foundation_model_b200 import ops
+from multi_modal_foundation_model_b200._lib import ACT_GELU, ACT_DGELU
+
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 51200
+NCOPY = 6
+dev = "cuda"
+bf = torch.bfloat16
+seed = torch.tensor([1], dtype=torch.int64, device=dev)
+
+
+def bench(name, fn, flops, bytes_, iters=30):
+    for i in range(3):
+        fn(i % NCOPY)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % NCOPY)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    print(f"{name:34s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {bytes_ / us / 1e3:7.1f} GB/s  (HBM floor {bytes_ / 6.544e6:6.1f} us)")
+
+
+def mk(r, c, dt=bf):
+    return [torch.randn(r, c, device=dev).to(dt) for _ in range(NCOPY)]
+
+
+H, I = 256, 512
+x = mk(R, H); w_qkv = mk(3 * H, H)[0]; qkv = mk(R, 3 * H)
+b768 = torch.randn(3 * H, device=dev); b256 = torch.randn(H, device=dev); b512 = torch.randn(I, device=dev)
+bench("qkv   [R,256]x[768,256] ->bf16", lambda i: ops.gemm_tn(x[i], w_qkv, qkv[i], bias=b768), 2.0 * R * 768 * 256, R * (256 * 2 + 768 * 2))
+res = mk(R, H, torch.float32); out = mk(R, H, torch.float32); w_o = mk(H, H)[0]
+bench("out   [R,256]x[256,256] +res ->f32", lambda i: ops.gemm_tn(x[i], w_o, out[i], bias=b256, res=res[i]), 2.0 * R * 256 * 256, R * (256 * 2 + 256 * 4 * 2))
+u = mk(R, I); g = mk(R, I); w_u = mk(I, H)[0]
+bench("up    [R,256]x[512,256] gelu+D2", lambda i: ops.gemm_tn(x[i], w_u, g[i], bias=b512, act=ACT_GELU, D2=u[i]), 2.0 * R * 512 * 256, R * (256 * 2 + 512 * 2 * 2))
+w_d = mk(H, I)[0]
+bench("down  [R,512]x[256,512] drop+res", lambda i: ops.gemm_tn(g[i], w_d, out[i], bias=b256, res=res[i], drop=ops.DropSpec(seed, 3, 0.4)), 2.0 * R * 256 * 512, R * (512 * 2 + 256 * 4 * 2))
+w_dT = mk(I, H)[0]
+bench("ddown [R,256]x[512,256] dgelu", lambda i: ops.gemm_tn(x[i], w_dT, g[i], act=ACT_DGELU, aux=u[i]), 2.0 * R * 512 * 256, R * (256 * 2 + 512 * 2 * 2))
+w_uT = mk(H, I)[0]
+bench("dup   [R,512]x[256,512] ->bf16", lambda i: ops.gemm_tn(g[i], w_uT, x[i]), 2.0 * R * 256 * 512, R * (512 * 2 + 256 * 2))
+w_qT = mk(H, 3 * H)[0]
+bench("dqkv  [R,768]x[256,768] ->bf16", lambda i: ops.gemm_tn(qkv[i], w_qT, x[i]), 2.0 * R * 256 * 768, R * (768 * 2 + 256 * 2))
+dW = torch.zeros(3 * H, H, device=dev); db = torch.zeros(3 * H, device=dev)
+bench("wgrad qkv dW[768,256]", lambda i: ops.gemm_wgrad(qkv[i], x[i], dW, dbias=db), 2.0 * R * 768 * 256, R * (768 * 2 + 256 * 2))
+dW2 = torch.zeros(H, I, device=dev); db2 = torch.zeros(H, device=dev)
+bench("wgrad down dW[256,512]", lambda i: ops.gemm_wgrad(x[i], g[i], dW2, dbias=db2), 2.0 * R * 256 * 512, R * (256 * 2 + 512 * 2))
+BT = R // 2
+xin = mk(BT, 672); w1 = mk(1336, 672)[0]; hid = mk(BT, 1336)
+bench("embed1 [BT,668]x[1336,668]", lambda i: ops.gemm_tn(xin[i][:, :668], w1[:, :668], hid[i]), 2.0 * BT * 1336 * 668, BT * (668 * 2 + 1336 * 2))
+bench("cuBLAS qkv (torch.matmul)", lambda i: torch.matmul(x[i], w_qkv.t(), out=qkv[i]), 2.0 * R * 768 * 256, R * (256 * 2 + 768 * 2))
