@@ -118,9 +118,17 @@ MMFM_DEVINL void mma_rowtile_nt(float (&acc)[8][4], const uint32_t (&a)[D / 16][
         const int c = ks * 16 + ((lane >> 3) & 1) * 8;
         ldsm_x4(b, stile + (uint32_t)(r * TileCfg<D>::kPitch + c) * 2);
         const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
-        mma_16816(acc[2 * np], a[ks], b0);
-        mma_16816(acc[2 * np + 1], a[ks], b1);
+        if (ks == 0) {   // the accumulator tile starts from zero: no clearing pass
+          mma_16816_z(acc[2 * np], a[ks], b0);
+          mma_16816_z(acc[2 * np + 1], a[ks], b1);
+        } else {
+          mma_16816(acc[2 * np], a[ks], b0);
+          mma_16816(acc[2 * np + 1], a[ks], b1);
+        }
       }
+    } else {
+      acc[2 * np][0] = acc[2 * np][1] = acc[2 * np][2] = acc[2 * np][3] = 0.f;
+      acc[2 * np + 1][0] = acc[2 * np + 1][1] = acc[2 * np + 1][2] = acc[2 * np + 1][3] = 0.f;
     }
   }
 }
@@ -231,6 +239,11 @@ MMFM_DEVINL uint32_t keep_bits16(const uint4& w, uint32_t thresh4) {
   return ((m0 * 0x01020408u) >> 24) | (((m1 * 0x01020408u) >> 24) << 4) | (((m2 * 0x01020408u) >> 24) << 8) |
          (((m3 * 0x01020408u) >> 24) << 12);
 }
+// 16 keep bits from four byte-mask words (0xFF / 0x00 per byte)
+MMFM_DEVINL uint32_t mask_bits16(const uint32_t (&m)[4]) {
+  return (((m[0] & 0x01010101u) * 0x01020408u) >> 24) | ((((m[1] & 0x01010101u) * 0x01020408u) >> 24) << 4) |
+         ((((m[2] & 0x01010101u) * 0x01020408u) >> 24) << 8) | ((((m[3] & 0x01010101u) * 0x01020408u) >> 24) << 12);
+}
 // 16 random bytes of the probability-dropout field: row = (b*nh+h)*Sq + i, 64-column block blk, quad lane ql
 MMFM_DEVINL uint4 pdrop_bytes(unsigned long long seed, uint32_t site, unsigned long long row, uint32_t nblk,
                               uint32_t blk, uint32_t ql) {
@@ -306,7 +319,7 @@ MMFM_DEVINL void mixed_bits(const AttnParams& p, const Blk& bk, int mode, int ql
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int D, bool DROP, bool SEP>
-__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, D == 32 ? 4 : 2) attn_fwd_kernel(const AttnParams p) {
   using TC = TileCfg<D>;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const uint32_t sQ = smem_u32(smem_dyn);
@@ -360,15 +373,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
     const Blk bk = classify<false>(mode, SEP, q0, kb * kTile, p.Sk, cvb, true, true);
     if (!bk.skip && warp_active) {
       const int npairs = (bk.ncols + 15) >> 4;
+      const int nt = 2 * npairs;
       float s[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
       mma_rowtile_nt<D>(s, qf, sK + st * TC::kBytes, lane, npairs);
       if (!bk.fast) {
         uint32_t a0, a1;
         mixed_bits<false, SEP>(p, bk, mode, ql, i0, kb * kTile, true, true, a0, a1);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
+          if (n >= nt) break;  // warp-uniform: columns past the block edge do no work
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             if (!((a0 >> (2 * n + e)) & 1u)) s[n][e] = -INFINITY;
@@ -379,6 +392,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
+        if (n >= nt) break;  // warp-uniform: columns past the block edge do no work
         mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
         mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
       }
@@ -392,6 +406,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
+        if (n >= nt) break;  // warp-uniform: columns past the block edge do no work
         s[n][0] = fast_exp2(fmaf(s[n][0], sl2, -base0));
         s[n][1] = fast_exp2(fmaf(s[n][1], sl2, -base0));
         s[n][2] = fast_exp2(fmaf(s[n][2], sl2, -base1));
@@ -405,22 +420,29 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const AttnParams
       for (int n = 0; n < D / 8; ++n) {
         o[n][0] *= al0; o[n][1] *= al0; o[n][2] *= al1; o[n][3] *= al1;
       }
+      uint32_t pf[4][4];
+      pack_p(s, pf);
       if (DROP) {
-        const uint32_t k0 = keep_bits16(pdrop_bytes(seed_p, p.drop_p.site, prow0, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql), thresh4);
-        const uint32_t k1 = keep_bits16(pdrop_bytes(seed_p, p.drop_p.site, prow0 + 8, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql), thresh4);
+        // keep decisions as byte masks (0xFF keep / 0x00 drop); survivors are rescaled once, on the output.
+        // Element (n-tile n, e) of row g reads byte 2n+e: word n/2, bytes 2(n%2)+e -> one PRMT widens two bytes into
+        // the two halves of the packed bf16x2 register, one LOP3 applies them.
+        const uint4 w0 = pdrop_bytes(seed_p, p.drop_p.site, prow0, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
+        const uint4 w1 = pdrop_bytes(seed_p, p.drop_p.site, prow0 + 8, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
+        const uint32_t ma[4] = {__vcmpgeu4(w0.x, thresh4), __vcmpgeu4(w0.y, thresh4), __vcmpgeu4(w0.z, thresh4),
+                                __vcmpgeu4(w0.w, thresh4)};
+        const uint32_t mb[4] = {__vcmpgeu4(w1.x, thresh4), __vcmpgeu4(w1.y, thresh4), __vcmpgeu4(w1.z, thresh4),
+                                __vcmpgeu4(w1.w, thresh4)};
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (!((k0 >> (2 * n + e)) & 1u)) s[n][e] = 0.f;        // survivors are rescaled once, on the output
-            if (!((k1 >> (2 * n + e)) & 1u)) s[n][2 + e] = 0.f;
-          }
+        for (int t = 0; t < 4; ++t) {
+          pf[t][0] &= __byte_perm(ma[t], 0u, 0x1100u);
+          pf[t][1] &= __byte_perm(mb[t], 0u, 0x1100u);
+          pf[t][2] &= __byte_perm(ma[t], 0u, 0x3322u);
+          pf[t][3] &= __byte_perm(mb[t], 0u, 0x3322u);
         }
+        const uint32_t k0 = mask_bits16(ma), k1 = mask_bits16(mb);
         if (i0 < p.Sq) p.p_keep[((bh * p.Sq + i0) * nkb + kb) * 4 + ql] = (unsigned short)k0;
         if (i0 + 8 < p.Sq) p.p_keep[((bh * p.Sq + i0 + 8) * nkb + kb) * 4 + ql] = (unsigned short)k1;
       }
-      uint32_t pf[4][4];
-      pack_p(s, pf);
       mma_rowtile_nn<D>(o, pf, sV + st * TC::kBytes, lane, npairs);
     }
     __syncthreads();
@@ -512,7 +534,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const AttnParams p) 
 // backward dQ: rows = queries, cols = keys
 // ------------------------------------------------------------------------------------------------------------
 template <int D, bool DROP, bool SEP>
-__global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, D == 32 ? 4 : 2) attn_bwd_dq_kernel(const AttnParams p) {
   using TC = TileCfg<D>;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const uint32_t sQ = smem_u32(smem_dyn), sdO = sQ + TC::kBytes;
@@ -568,12 +590,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
     const Blk bk = classify<false>(mode, SEP, q0, kb * kTile, p.Sk, cvb, true, true);
     if (!bk.skip && warp_active) {
       const int npairs = (bk.ncols + 15) >> 4;
+      const int nt = 2 * npairs;
       float s[8][4], dp[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-      }
       mma_rowtile_nt<D>(s, qf, sK + st * TC::kBytes, lane, npairs);
       mma_rowtile_nt<D>(dp, dof, sV + st * TC::kBytes, lane, npairs);
       uint32_t a0 = 0xFFFFu, a1 = 0xFFFFu;
@@ -585,6 +603,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
       }
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
+        if (n >= nt) break;  // warp-uniform: columns past the block edge do no work
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int bit = 2 * n + e;
@@ -627,7 +646,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dq_kernel(const AttnPar
 // backward dK, dV: rows = keys, cols = queries
 // ------------------------------------------------------------------------------------------------------------
 template <int D, bool DROP, bool SEP>
-__global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, D == 32 ? 3 : 2) attn_bwd_dkv_kernel(const AttnParams p) {
   using TC = TileCfg<D>;
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   const uint32_t sK = smem_u32(smem_dyn), sV = sK + TC::kBytes;
@@ -712,12 +731,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
     const Blk bk = classify<true>(mode, SEP, k0, qb * kTile, p.Sq, 0ull, rows_all_valid, rows_any_valid);
     if (!bk.skip && warp_active) {
       const int npairs = (bk.ncols + 15) >> 4;
+      const int nt = 2 * npairs;
       float s[8][4], dp[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-      }
       mma_rowtile_nt<D>(s, kf, sQ + st * TC::kBytes, lane, npairs);     // S^T[key, query]
       mma_rowtile_nt<D>(dp, vf, sdO + st * TC::kBytes, lane, npairs);   // dP^T[key, query]
       uint32_t a0 = 0xFFFFu, a1 = 0xFFFFu;
@@ -728,6 +743,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_dkv_kernel(const AttnPa
       const unsigned short* kp = sKeep + (st * kTile + 2 * ql) * 4 + kq;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
+        if (n >= nt) break;  // warp-uniform: columns past the block edge do no work
         const float2 lse2 = *reinterpret_cast<const float2*>(lsep + 8 * n);
         const float2 dl2 = *reinterpret_cast<const float2*>(dlp + 8 * n);
 #pragma unroll

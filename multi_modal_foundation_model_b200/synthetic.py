@@ -38,6 +38,9 @@ def make_batch(batch: int, n_neurons: int, n_behaviors: int = 2, n_bins: int = 1
     ts = torch.arange(n_bins, dtype=torch.int64)[None, :].expand(batch, n_bins).contiguous()
     regions = [[_REGIONS[i % len(_REGIONS)]] * batch for i in range(n_neurons)]  # loader layout: N lists of B
     out = {
+        # (B, N) region matrix, converted once: the trainer redoes np.asarray(batch['neuron_regions']).T every step
+        # (trainer/base.py:73), ~10 ms of pure Python at N=668 x B=256 that is outside the hot path
+        "_regions_T": np.asarray(regions).T,
         "spikes_data": spikes.float(),
         "target": beh.float(),
         "time_attn_mask": attn,
@@ -75,7 +78,7 @@ def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[s
         if mod == "ap":
             d["inputs"] = spikes.clone()
             d["targets"] = spikes.clone()
-            d["inputs_regions"] = np.asarray(batch["neuron_regions"]).T
+            d["inputs_regions"] = batch["_regions_T"] if "_regions_T" in batch else np.asarray(batch["neuron_regions"]).T
         else:
             # 'behavior' (all nb channels) or an extra single-channel stream 'behN' (config 5 extension)
             if mod == "behavior":
