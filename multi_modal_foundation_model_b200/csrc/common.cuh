@@ -212,11 +212,27 @@ MMFM_DEVINL uint32_t drop_byte(const uint4& w, int b) {  // b in [0,16)
 // ------------------------------------------------------------------------------------------------
 // small math
 // ------------------------------------------------------------------------------------------------
-MMFM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU (transformers ACT2FN['gelu'], mm_utils.py:46) through Abramowitz-Stegun 7.1.26: |erf error| <= 1.5e-7,
+// far below the bf16 rounding of the outputs, at roughly half the instructions of erff(); e = exp(-x^2/2) is shared
+// with the derivative's Gaussian term.
+MMFM_DEVINL float erf_poly(float z, float& e) {   // returns erf(z); e = exp(-z*z)
+  const float az = fabsf(z);
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * z * z));
+  e = ex;
+  const float poly =
+      fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  return copysignf(fmaf(-poly, ex, 1.0f), z);
+}
+MMFM_DEVINL float gelu_erf(float x) {
+  float e;
+  return 0.5f * x * (1.0f + erf_poly(x * 0.70710678118654752f, e));
+}
 MMFM_DEVINL float gelu_erf_grad(float x) {
-  float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_poly(x * 0.70710678118654752f, e));
+  return fmaf(x * 0.3989422804014327f, e, cdf);   // Phi(x) + x * phi(x), phi(x) = exp(-x^2/2) / sqrt(2 pi)
 }
 MMFM_DEVINL float softsign(float x) { return x / (1.0f + fabsf(x)); }
 

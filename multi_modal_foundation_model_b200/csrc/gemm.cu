@@ -72,7 +72,7 @@ MMFM_DEVINL void st4_bf16(bf16* p, bool vec, int nvalid, const float4& v) {
 // lane quadrant, each taking one half of the tile's columns).  The epilogue flavour is a template parameter so the
 // per-element code is branch-free; EPI_GENERIC keeps every run-time option (unaligned pitches, odd N).
 // ------------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;   // four warps per TMEM lane quadrant, each taking a quarter of the tile's columns
 constexpr int kTnThreads = 64 + kEpiWarps * 32;
 
 enum EpiKind : int {
@@ -86,32 +86,34 @@ enum EpiKind : int {
   EPI_GENERIC = 7
 };
 
+// Persistent: one CTA per SM walks the tile list (n fastest, so concurrently running CTAs share A rows in L2).  The
+// TMA producer runs ahead across tile boundaries through a STAGES-deep ring; the accumulator is double-buffered in
+// TMEM (2 x BN columns) so the MMA of tile i+1 overlaps the epilogue of tile i; the epilogue stages through its own
+// shared-memory tile.
 template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(kTnThreads, 2) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
-                                                                 const mmfm_gemm_args p) {
+                                                                 const mmfm_gemm_args p, int tiles_n, int n_tiles) {
   constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
   constexpr uint32_t kBBytes = BN * kBK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 256 or 128: power of two
   constexpr int kPitch = BN + 4;  // fp32 staging pitch (floats): 16-byte rows, conflict-free in both phases
-  constexpr int kHalf = BN / 2;   // columns per epilogue warp
-  static_assert((size_t)kBM * kPitch * 4 <= (size_t)STAGES * kStageBytes, "staging tile must fit in the stages");
+  constexpr int kHalf = BN / (kEpiWarps / 4);   // columns per epilogue warp
   constexpr bool GEN = EPI == EPI_GENERIC;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_bias[BN];
+  __shared__ __align__(16) float s_bias[kEpiWarps][kHalf];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  float* stage_f = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+  float* stage_f = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + STAGES * kStageBytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
   const int nkb = (p.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -122,16 +124,15 @@ __global__ void __launch_bounds__(kTnThreads, 2) gemm_tn_kernel(const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], kEpiWarps);
+    mbar_init(&acc_empty[1], kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc(&tmem_slot, kTmemCols);
     tmem_relinquish();
-  }
-  if (warp >= 2) {
-    for (int c = threadIdx.x - 64; c < BN; c += kEpiWarps * 32)
-      s_bias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -140,182 +141,222 @@ __global__ void __launch_bounds__(kTnThreads, 2) gemm_tn_kernel(const __grid_con
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(&empty_bar[s], ((kb / STAGES) - 1) & 1);
-        mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        const uint32_t a_dst = smem_base + s * kStageBytes;
-        tma_load_2d_addr(a_dst, &tmA, &full_bar[s], kb * kBK, m0);
-        tma_load_2d_addr(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          tma_load_2d_addr(a_dst, &tmA, &full_bar[s], kb * kBK, m0);
+          tma_load_2d_addr(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const uint32_t buf = t & 1u;
+        if (t >= 2) mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1);   // epilogue drained this TMEM buffer
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * kStageBytes;
-        const uint32_t b_addr = a_addr + kABytes;
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + s * kStageBytes;
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(&accum_bar);
     }
   } else {
-    // ---------------- epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 ----------
+    // ---------------- epilogue warps: TMEM lane quadrant = warp % 4, column slice = (warp - 2) / 4 ----------
+    const int ew = warp - 2;
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = ew >> 2;
     const int cbase = half * kHalf;
     const int row_l = quad * 32 + lane;            // tile row of this thread (phase A)
-    const long long r = (long long)m0 + row_l;     // GEMM row
     constexpr bool kMayDrop = GEN || EPI == EPI_RES_F32;
     constexpr bool kHasRes = GEN || EPI == EPI_RES_F32;
     constexpr bool kHasAux = GEN || EPI == EPI_DGELU || EPI == EPI_DSOFTSIGN;
-    bool zero = false;
     bool drop = false;
     unsigned long long seed = 0ull;
     if (kMayDrop) {
-      if (p.row_zero && r < p.M) {
-        const int pos = p.remap_T > 0 ? p.remap_off + (int)(r % p.remap_T) : (int)(r % p.remap_S);
-        zero = p.row_zero[pos] != 0;
-      }
       drop = p.drop.thresh != 0u;
       if (drop) seed = *p.drop.seed;
     }
     const uint32_t drop_gpr = (uint32_t)((p.N + 15) >> 4);
-    const bool warp_has_cols = (n0 + cbase) < p.N;
+    const int act = GEN ? p.act : 0;
+    const bool f32out = GEN ? (p.d_fp32 != 0) : (EPI == EPI_PLAIN_F32 || EPI == EPI_RES_F32);
+    const float inv_scale = 1.0f / p.act_scale;
+    const bool has_res = GEN ? (p.res != nullptr) : (EPI == EPI_RES_F32);
+    const bool has_aux = GEN ? (act == MMFM_ACT_DGELU || act == MMFM_ACT_DSOFTSIGN) : kHasAux;
+    float* my_bias = s_bias[ew];
+    static_assert(kHalf <= 64, "bias slice: at most two values per lane");
+    // bias slice of this warp's columns, fetched one tile ahead so its latency is never exposed
+    auto load_bias = [&](int tile_i, float (&b)[2]) {
+      b[0] = b[1] = 0.f;
+      if (tile_i < n_tiles && p.bias) {
+        const int nn = (tile_i % tiles_n) * BN + cbase;
+        if (lane < kHalf && nn + lane < p.N) b[0] = __ldg(p.bias + nn + lane);
+        if (lane + 32 < kHalf && nn + lane + 32 < p.N) b[1] = __ldg(p.bias + nn + lane + 32);
+      }
+    };
+    float bias_next[2];
+    load_bias(blockIdx.x, bias_next);
 
-    // while the main loop runs: pull this thread's residual / saved-tensor row segment into L2
-    if (r < p.M && warp_has_cols) {
-      const int ncols = min(kHalf, p.N - n0 - cbase);
-      if (kHasRes && p.res) {
-        long long orow = r;
-        if (p.remap_T > 0) {
-          const int bb = (int)r / p.remap_T;
-          orow = (long long)bb * p.remap_S + p.remap_off + ((int)r - bb * p.remap_T);
-        }
-        const char* ptr = reinterpret_cast<const char*>(p.res + orow * p.ldr + n0 + cbase);
-        for (int o = 0; o < ncols * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1u;
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+      const long long r = (long long)m0 + row_l;     // GEMM row of this thread in phase A
+      const bool warp_has_cols = (n0 + cbase) < p.N;
+      if (lane < kHalf) my_bias[lane] = bias_next[0];
+      if (lane + 32 < kHalf) my_bias[lane + 32] = bias_next[1];
+      load_bias(tile + gridDim.x, bias_next);
+      bool zero = false;
+      if (kMayDrop && p.row_zero && r < p.M) {
+        const int pos = p.remap_T > 0 ? p.remap_off + (int)(r % p.remap_T) : (int)(r % p.remap_S);
+        zero = p.row_zero[pos] != 0;
       }
-      if (kHasAux && p.aux) {
-        const char* ptr =
-            reinterpret_cast<const char*>(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + n0 + cbase);
-        for (int o = 0; o < ncols * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
-      }
-    }
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    if (warp_has_cols) {
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase;
-      float* my_row = stage_f + row_l * kPitch + cbase;
-      // ---------------- phase A: thread = row ----------------
-#pragma unroll
-      for (int c0 = 0; c0 < kHalf; c0 += 16) {
-        uint32_t acc[16];
-        tmem_ld16(t_row + (uint32_t)c0, acc);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + j4 * 4]);
-          v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b4.x;
-          v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b4.y;
-          v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b4.z;
-          v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b4.w;
-        }
-        if (kMayDrop) {
-          if (drop) {
-            const uint4 w = drop_bytes16(seed, p.drop.site, (uint64_t)r, drop_gpr, (uint32_t)((n0 + cbase + c0) >> 4));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = (drop_byte(w, j) < p.drop.thresh) ? 0.f : v[j] * p.drop.scale;
+      // while the main loop runs: pull this thread's residual / saved-tensor row segment into L2
+      if (r < p.M && warp_has_cols) {
+        const int ncols = min(kHalf, p.N - n0 - cbase);
+        if (kHasRes && p.res) {
+          long long orow = r;
+          if (p.remap_T > 0) {
+            const int bb = (int)r / p.remap_T;
+            orow = (long long)bb * p.remap_S + p.remap_off + ((int)r - bb * p.remap_T);
           }
-          if (zero) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          }
+          const char* ptr = reinterpret_cast<const char*>(p.res + orow * p.ldr + n0 + cbase);
+          for (int o = 0; o < ncols * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
         }
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          *reinterpret_cast<float4*>(my_row + c0 + j4 * 4) =
-              make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        if (kHasAux && p.aux) {
+          const char* ptr =
+              reinterpret_cast<const char*>(reinterpret_cast<const bf16*>(p.aux) + r * p.ldaux + n0 + cbase);
+          for (int o = 0; o < ncols * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + o));
+        }
       }
       __syncwarp();
-      // ---------------- phase B: lane = 4 consecutive columns; coalesced global traffic ----------------
-      constexpr int kLanesPerRow = kHalf / 4;          // 16 (BN 128) or 8 (BN 64)
-      constexpr int kRowsPerStep = 32 / kLanesPerRow;  // 2 or 4
-      constexpr int kSteps = 32 / kRowsPerStep;        // 16 or 8
-      constexpr int kBatch = 8;                        // steps whose global loads are issued together
-      const int lcol = cbase + (lane % kLanesPerRow) * 4;
-      const int n = n0 + lcol;
-      const int nvalid = p.N - n;
-      const int lrow = lane / kLanesPerRow;
-      const int act = GEN ? p.act : 0;
-      const bool f32out = GEN ? (p.d_fp32 != 0) : (EPI == EPI_PLAIN_F32 || EPI == EPI_RES_F32);
-      // the specialised kernels are only launched when every pointer / pitch is vector-aligned and N % 4 == 0
-      const bool vec_d = GEN ? ((p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D) & (p.d_fp32 ? 15 : 7)) == 0)) : true;
-      const bool vec_d2 = GEN ? (p.D2 && (p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D2) & 7) == 0)) : true;
-      const bool vec_r = GEN ? (p.res && (p.ldr % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)) : true;
-      const bool vec_a = GEN ? (p.aux && (p.ldaux % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0)) : true;
-      const float inv_scale = 1.0f / p.act_scale;
-      const bool has_res = GEN ? (p.res != nullptr) : (EPI == EPI_RES_F32);
-      const bool has_aux = GEN ? (act == MMFM_ACT_DGELU || act == MMFM_ACT_DSOFTSIGN) : kHasAux;
-      if (nvalid > 0) {
-#pragma unroll 1
-        for (int it0 = 0; it0 < kSteps; it0 += kBatch) {
-          float4 rv[kBatch], av[kBatch];
-          long long orow[kBatch];
+      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      if (warp_has_cols) {
+        const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase;
+        float* my_row = stage_f + row_l * kPitch + cbase;
+        // ---------------- phase A: thread = row ----------------
 #pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
-            const long long rr = (long long)m0 + rl;
-            orow[u] = rr;
-            if (kMayDrop && p.remap_T > 0) {
-              const int bb = (int)rr / p.remap_T;
-              orow[u] = (long long)bb * p.remap_S + p.remap_off + ((int)rr - bb * p.remap_T);
+        for (int c0 = 0; c0 < kHalf; c0 += 16) {
+          uint32_t acc[16];
+          tmem_ld16(t_row + (uint32_t)c0, acc);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&my_bias[c0 + j4 * 4]);
+            v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b4.x;
+            v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b4.y;
+            v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b4.z;
+            v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b4.w;
+          }
+          if (kMayDrop) {
+            if (drop) {
+              const uint4 w = drop_bytes16(seed, p.drop.site, (uint64_t)r, drop_gpr, (uint32_t)((n0 + cbase + c0) >> 4));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (drop_byte(w, j) < p.drop.thresh) ? 0.f : v[j] * p.drop.scale;
             }
-            if (rr >= p.M) orow[u] = -1;
-            rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            av[u] = rv[u];
-            if (orow[u] >= 0) {
-              if (has_res) rv[u] = ld4_f32(p.res + orow[u] * p.ldr + n, vec_r, nvalid);
-              if (has_aux) av[u] = ld4_bf16(reinterpret_cast<const bf16*>(p.aux) + rr * p.ldaux + n, vec_a, nvalid);
+            if (zero) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
           }
 #pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            if (orow[u] < 0) continue;
-            const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
-            float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
-            if (EPI == EPI_GELU || (GEN && act == MMFM_ACT_GELU)) {
-              if (!GEN || p.D2) st4_bf16(reinterpret_cast<bf16*>(p.D2) + orow[u] * p.ldd + n, vec_d2, nvalid, v);
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            } else if (EPI == EPI_SOFTSIGN || (GEN && act == MMFM_ACT_SOFTSIGN)) {
-              v.x = softsign(v.x) * p.act_scale; v.y = softsign(v.y) * p.act_scale;
-              v.z = softsign(v.z) * p.act_scale; v.w = softsign(v.w) * p.act_scale;
-            } else if (EPI == EPI_DGELU || (GEN && act == MMFM_ACT_DGELU)) {
-              const float4 a = av[u];
-              v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(a.z); v.w *= gelu_erf_grad(a.w);
-            } else if (EPI == EPI_DSOFTSIGN || (GEN && act == MMFM_ACT_DSOFTSIGN)) {
-              const float4 a = av[u];
-              float t;
-              t = 1.0f - fabsf(a.x * inv_scale); v.x *= p.act_scale * t * t;
-              t = 1.0f - fabsf(a.y * inv_scale); v.y *= p.act_scale * t * t;
-              t = 1.0f - fabsf(a.z * inv_scale); v.z *= p.act_scale * t * t;
-              t = 1.0f - fabsf(a.w * inv_scale); v.w *= p.act_scale * t * t;
+          for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4*>(my_row + c0 + j4 * 4) =
+                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+      }
+      // this warp is done with the TMEM buffer: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (warp_has_cols) {
+        // ---------------- phase B: lane = 4 consecutive columns; coalesced global traffic ----------------
+        constexpr int kLanesPerRow = kHalf / 4;          // 8 (BN 128) or 4 (BN 64)
+        constexpr int kRowsPerStep = 32 / kLanesPerRow;  // 4 or 8
+        constexpr int kSteps = 32 / kRowsPerStep;        // 8 or 4
+        constexpr int kBatch = kSteps < 8 ? kSteps : 8;  // steps whose global loads are issued together
+        const int lcol = cbase + (lane % kLanesPerRow) * 4;
+        const int n = n0 + lcol;
+        const int nvalid = p.N - n;
+        const int lrow = lane / kLanesPerRow;
+        // the specialised kernels are only launched when every pointer / pitch is vector-aligned and N % 4 == 0
+        const bool vec_d = GEN ? ((p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D) & (p.d_fp32 ? 15 : 7)) == 0)) : true;
+        const bool vec_d2 = GEN ? (p.D2 && (p.ldd % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.D2) & 7) == 0)) : true;
+        const bool vec_r = GEN ? (p.res && (p.ldr % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0)) : true;
+        const bool vec_a = GEN ? (p.aux && (p.ldaux % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0)) : true;
+        if (nvalid > 0) {
+#pragma unroll 1
+          for (int it0 = 0; it0 < kSteps; it0 += kBatch) {
+            float4 rv[kBatch], av[kBatch];
+            long long orow[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
+              const long long rr = (long long)m0 + rl;
+              orow[u] = rr;
+              if (kMayDrop && p.remap_T > 0) {
+                const int bb = (int)rr / p.remap_T;
+                orow[u] = (long long)bb * p.remap_S + p.remap_off + ((int)rr - bb * p.remap_T);
+              }
+              if (rr >= p.M) orow[u] = -1;
+              rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              av[u] = rv[u];
+              if (orow[u] >= 0) {
+                if (has_res) rv[u] = ld4_f32(p.res + orow[u] * p.ldr + n, vec_r, nvalid);
+                if (has_aux) av[u] = ld4_bf16(reinterpret_cast<const bf16*>(p.aux) + rr * p.ldaux + n, vec_a, nvalid);
+              }
             }
-            if (has_res) { v.x += rv[u].x; v.y += rv[u].y; v.z += rv[u].z; v.w += rv[u].w; }
-            if (f32out) st4_f32(reinterpret_cast<float*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
-            else st4_bf16(reinterpret_cast<bf16*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+              if (orow[u] < 0) continue;
+              const int rl = quad * 32 + (it0 + u) * kRowsPerStep + lrow;
+              float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
+              if (EPI == EPI_GELU || (GEN && act == MMFM_ACT_GELU)) {
+                if (!GEN || p.D2) st4_bf16(reinterpret_cast<bf16*>(p.D2) + orow[u] * p.ldd + n, vec_d2, nvalid, v);
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+              } else if (EPI == EPI_SOFTSIGN || (GEN && act == MMFM_ACT_SOFTSIGN)) {
+                v.x = softsign(v.x) * p.act_scale; v.y = softsign(v.y) * p.act_scale;
+                v.z = softsign(v.z) * p.act_scale; v.w = softsign(v.w) * p.act_scale;
+              } else if (EPI == EPI_DGELU || (GEN && act == MMFM_ACT_DGELU)) {
+                const float4 a = av[u];
+                v.x *= gelu_erf_grad(a.x); v.y *= gelu_erf_grad(a.y); v.z *= gelu_erf_grad(a.z); v.w *= gelu_erf_grad(a.w);
+              } else if (EPI == EPI_DSOFTSIGN || (GEN && act == MMFM_ACT_DSOFTSIGN)) {
+                const float4 a = av[u];
+                float tt;
+                tt = 1.0f - fabsf(a.x * inv_scale); v.x *= p.act_scale * tt * tt;
+                tt = 1.0f - fabsf(a.y * inv_scale); v.y *= p.act_scale * tt * tt;
+                tt = 1.0f - fabsf(a.z * inv_scale); v.z *= p.act_scale * tt * tt;
+                tt = 1.0f - fabsf(a.w * inv_scale); v.w *= p.act_scale * tt * tt;
+              }
+              if (has_res) { v.x += rv[u].x; v.y += rv[u].y; v.z += rv[u].z; v.w += rv[u].w; }
+              if (f32out) st4_f32(reinterpret_cast<float*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
+              else st4_bf16(reinterpret_cast<bf16*>(p.D) + orow[u] * p.ldd + n, vec_d, nvalid, v);
+            }
           }
         }
       }
+      __syncwarp();   // phase B reads of the staging rows are done before the next tile's phase A overwrites them
     }
   }
   tc_fence_before();
@@ -553,15 +594,17 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, kBK, BN, TMA_SW_128);
   if (rc) return rc;
-  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + (size_t)kBM * (BN + 4) * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
     attr_set = true;
   }
-  dim3 grid((a->N + BN - 1) / BN, (a->M + kBM - 1) / kBM, 1);
-  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a);
+  const int tiles_n = (a->N + BN - 1) / BN;
+  const int n_tiles = tiles_n * ((a->M + kBM - 1) / kBM);
+  const int grid = n_tiles < device_sm_count() ? n_tiles : device_sm_count();
+  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a, tiles_n, n_tiles);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -569,7 +612,7 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
 template <int EPI>
 static int launch_tn_bn(const mmfm_gemm_args* a, cudaStream_t st) {
   if (a->N <= 64) return launch_tn<64, 4, EPI>(a, st);
-  return launch_tn<128, 3, EPI>(a, st);
+  return launch_tn<128, 4, EPI>(a, st);
 }
 
 static bool al(const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; }

@@ -125,8 +125,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
     const float* xr = x + r * H;
     const bf16* dyr = dy + ln_out_row(r, modmajor_T, S, BT) * H;
     const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-    float4 xh[NV], gd[NV];
+    float4 xh[NV], gd[NV], dr[NV];
     float s1 = 0.f, s2 = 0.f;
+    if (dres) {   // issued up front: in flight together with x / dy instead of after the two reductions
+#pragma unroll
+      for (int j = 0; j < NV; ++j) dr[j] = reinterpret_cast<const float4*>(dres + r * H)[lane + 32 * j];
+    }
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const float4 xv = __ldg(reinterpret_cast<const float4*>(xr) + lane + 32 * j);
@@ -148,10 +152,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
       o.y = rs * (gd[j].y - m1 - xh[j].y * m2);
       o.z = rs * (gd[j].z - m1 - xh[j].z * m2);
       o.w = rs * (gd[j].w - m1 - xh[j].w * m2);
-      if (dres) {
-        const float4 dr = reinterpret_cast<const float4*>(dres + r * H)[lane + 32 * j];
-        o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
-      }
+      if (dres) { o.x += dr[j].x; o.y += dr[j].y; o.z += dr[j].z; o.w += dr[j].w; }
       if (dx) reinterpret_cast<float4*>(dx + r * H)[lane + 32 * j] = o;
       if (dxb) {
         if (drop.thresh != 0u) {
@@ -198,9 +199,16 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
 using namespace mmfm;
 
 static int ln_grid(int R) {
-  const int want = (R + kLnWarps - 1) / kLnWarps;
-  const int cap = device_sm_count() * 8;
-  return want < cap ? want : cap;
+  // one row per warp, no cap: the block scheduler balances better than a grid-stride loop with a ragged tail
+  return (R + kLnWarps - 1) / kLnWarps;
+}
+
+// CTAs that are resident at once (whole waves only: the backward ends with per-CTA atomics, so fat CTAs)
+template <typename K>
+static int resident_ctas(K kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * device_sm_count();
 }
 
 extern "C" int mmfm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean,
@@ -241,14 +249,16 @@ extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* m
     dc = DropCfg{drop->seed, drop->site, drop->thresh, drop->scale};
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // fewer, fatter CTAs than the forward: every CTA ends with 2*H atomics
-  int grid = (R + kLnWarps * 8 - 1) / (kLnWarps * 8);
-  const int cap = device_sm_count() * 4;
-  if (grid > cap) grid = cap;
-  if (grid < 1) grid = 1;
-#define LN_BWD(NV)                                                                                             \
-  layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const bf16*)dy, x, mean, rstd, gamma, dres, dx, \
-                                                            (bf16*)dxb, dc, dgamma, dbeta, R, H, modmajor_T, S)
+  // fewer, fatter CTAs than the forward (every CTA ends with 2*H atomics); exactly one resident wave
+  const int want = (R + kLnWarps * 4 - 1) / (kLnWarps * 4);
+#define LN_BWD(NV)                                                                                                \
+  do {                                                                                                            \
+    static int cap = 0;                                                                                           \
+    if (cap == 0) cap = resident_ctas(layernorm_bwd_kernel<NV>, kLnWarps * 32);                                   \
+    const int grid = want < cap ? (want < 1 ? 1 : want) : cap;                                                    \
+    layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const bf16*)dy, x, mean, rstd, gamma, dres, dx,     \
+                                                              (bf16*)dxb, dc, dgamma, dbeta, R, H, modmajor_T, S); \
+  } while (0)
   switch (H) {
     case 128: LN_BWD(1); break;
     case 256: LN_BWD(2); break;
