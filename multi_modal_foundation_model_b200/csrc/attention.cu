@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "../../include/mmfm_b200.h"
+#include <stdlib.h>
 
 namespace mmfm {
 
@@ -797,6 +798,237 @@ __global__ void __launch_bounds__(kAttnThreads, D == 32 ? 3 : 2) attn_bwd_dkv_ke
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// forward, tcgen05 / TMEM variant for Sk <= 256 (the model's S = n_mod * T = 200): the whole key range is one tile,
+// so the softmax is a single exact pass and the kernel is:
+//   TMA (Q 128 x D, K Npad x D, V Npad x D, swizzled)  ->  tcgen05.mma  S[128, Npad] = Q K^T  (fp32 in TMEM)
+//   4 warps, THREAD = QUERY ROW (TMEM lane): tcgen05.ld the row in 32-column chunks, mask from a per-chunk 32-bit
+//   word (key-validity bits | diagonal bit / causal prefix), max, exp2, sum, dropout on the packed bf16 pairs,
+//   tcgen05.st of P (bf16, two K elements per 32-bit column) OVER the already-consumed part of S
+//   tcgen05.mma  O[128, D] = P (A operand read from TMEM) . V (MN-major smem operand)   ->  scale, output dropout, store
+// No quad shuffles, no online rescaling, ~3x fewer instructions per score element than the mma.sync kernel.
+// The dropout field and the stored keep words are bit-identical to the flash kernel's (same Philox calls), so the
+// mma.sync backward kernels consume them unchanged.
+// ------------------------------------------------------------------------------------------------------------
+template <int D, bool DROP>
+__global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV, const AttnParams p,
+                                                          int npad, int tmem_cols) {
+  constexpr uint32_t kRowBytes = D * 2;                    // 64 (64B swizzle) or 128 (128B swizzle)
+  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;        // UMMA smem-descriptor swizzle code
+  constexpr uint32_t kSbo = 8 * kRowBytes;                 // 8-row swizzle atom
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t ld_bar, s_bar, o_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_colbits[8];
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sK = sQ + 128 * kRowBytes, sV = sK + 256 * kRowBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int mode = p.mask_mode;
+  const long long bh = (long long)(b * p.nh + h);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&ld_bar, 1);
+    mbar_init(&s_bar, 1);
+    mbar_init(&o_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
+    tmem_relinquish();
+  }
+  {
+    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
+    for (int w = warp; w < 8; w += 4) {
+      const int j = w * 32 + lane;
+      const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
+      const uint32_t m = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_colbits[w] = m;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((128 + 2 * npad) * kRowBytes));
+      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
+      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
+      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
+      mbar_wait(&ld_bar, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k) {
+        const uint64_t da = make_smem_desc(sQ + k * 32, 16, kSbo, kLayout);
+        const uint64_t db = make_smem_desc(sK + k * 32, 16, kSbo, kLayout);
+        umma_bf16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(&s_bar);
+    }
+    __syncwarp();
+  }
+
+  // ---------------- softmax: thread = query row ----------------
+  const int i = q0 + tid;
+  const float sl2 = p.scale * kLog2e;
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int nch = (npad + 31) >> 5;      // 32-column chunks
+  const int nkb = (p.Sk + kTile - 1) / kTile;
+  mbar_wait(&s_bar, 0);
+  tc_fence_after();
+
+  auto allowed_word = [&](int c) -> uint32_t {
+    uint32_t aw = s_colbits[c];
+    const int rel = i - 32 * c;
+    if (mode == MMFM_MASK_KEY_OR_DIAG) {
+      if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
+    } else if (mode == MMFM_MASK_CAUSAL) {
+      aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
+    }
+    return aw;
+  };
+
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_row + 32u * c, r);
+    tmem_ld_wait();
+    const uint32_t aw = allowed_word(c);
+    if (aw == 0xFFFFFFFFu) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if ((aw >> k) & 1u) mx = fmaxf(mx, __uint_as_float(r[k]));
+    }
+  }
+  const float base = (mx == -INFINITY) ? 0.f : mx * sl2;
+  float l = 0.f;
+  unsigned long long seed_p = 0ull;
+  uint32_t thresh4 = 0;
+  if (DROP) {
+    seed_p = *p.drop_p.seed;
+    thresh4 = p.drop_p.thresh * 0x01010101u;
+  }
+  const unsigned long long prow = (unsigned long long)bh * p.Sq + i;
+  uint32_t mw[4][4];   // keep byte-masks of the current 64-column block: [quad lane ql][word]
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_row + 32u * c, r);
+    tmem_ld_wait();
+    const uint32_t aw = allowed_word(c);
+    float pv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float e = fast_exp2(fmaf(__uint_as_float(r[k]), sl2, -base));
+      if (aw != 0xFFFFFFFFu && !((aw >> k) & 1u)) e = 0.f;
+      pv[k] = e;
+      l += e;
+    }
+    uint32_t pk[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) pk[t] = pack_bf16x2(pv[2 * t], pv[2 * t + 1]);
+    if (DROP) {
+      const int kb = c >> 1, hf = c & 1;
+      if (hf == 0) {
+#pragma unroll
+        for (int ql = 0; ql < 4; ++ql) {
+          const uint4 w = pdrop_bytes(seed_p, p.drop_p.site, prow, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
+          mw[ql][0] = __vcmpgeu4(w.x, thresh4);
+          mw[ql][1] = __vcmpgeu4(w.y, thresh4);
+          mw[ql][2] = __vcmpgeu4(w.z, thresh4);
+          mw[ql][3] = __vcmpgeu4(w.w, thresh4);
+        }
+        if (i < p.Sq) {
+          const uint32_t lo = mask_bits16(mw[0]) | (mask_bits16(mw[1]) << 16);
+          const uint32_t hi = mask_bits16(mw[2]) | (mask_bits16(mw[3]) << 16);
+          *reinterpret_cast<uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + kb) * 4) = make_uint2(lo, hi);
+        }
+      }
+      // pair t covers columns 32c + 2t, +1: n-tile n = 4*hf + t/4, quad lane ql = t%4 -> bytes 2n, 2n+1 of call ql
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int wsel = t >> 3;                                   // word (n >> 1) = 2*hf + t/8
+        const uint32_t wlo = mw[t & 3][wsel], whi = mw[t & 3][2 + wsel];
+        const uint32_t word = hf ? whi : wlo;
+        pk[t] &= ((t >> 2) & 1) ? __byte_perm(word, 0u, 0x3322u) : __byte_perm(word, 0u, 0x1100u);
+      }
+    }
+    tmem_st16(t_row + 16u * c, pk);   // P chunk c aliases S columns [16c, 16c+16), all of them already consumed
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+
+  const uint32_t o_col = (uint32_t)npad;
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);   // A (TMEM) K-major, B = V MN-major
+      const int nks = npad >> 4;
+      for (int kk = 0; kk < nks; ++kk) {
+        const uint64_t db = make_smem_desc(sV + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout);
+        umma_bf16_ts(tmem_base + o_col, tmem_base + 8u * kk, db, idesc, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(&o_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&o_bar, 0);
+  tc_fence_after();
+
+  // ---------------- epilogue: O row -> scale, output dropout, store ----------------
+  float inv = l > 0.f ? 1.0f / l : 0.f;
+  if (i < p.Sq) p.lse[bh * p.Sq + i] = (l > 0.f) ? (base + log2f(l)) * kLn2 : -INFINITY;
+  if (DROP) inv *= p.drop_p.scale;
+  const bool drop_o = p.drop_o.thresh != 0u;
+  unsigned long long seed_o = 0ull;
+  if (drop_o) seed_o = *p.drop_o.seed;
+  const uint32_t gpr_o = (uint32_t)((p.nh * D + 15) >> 4);
+#pragma unroll
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(t_row + o_col + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (i < p.Sq) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) * inv;
+      const int col = h * D + c0;
+      if (drop_o) {
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          const uint4 w = drop_bytes16(seed_o, p.drop_o.site, (uint64_t)((long long)b * p.Sq + i), gpr_o,
+                                       (uint32_t)((col + 16 * g16) >> 4));
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            v[16 * g16 + k] = drop_byte(w, k) < p.drop_o.thresh ? 0.f : v[16 * g16 + k] * p.drop_o.scale;
+        }
+      }
+      bf16* dst = p.o + ((long long)b * p.Sq + i) * p.ldo + col;
+#pragma unroll
+      for (int k = 0; k < 32; k += 8)
+        *reinterpret_cast<uint4*>(dst + k) = make_uint4(pack_bf16x2(v[k], v[k + 1]), pack_bf16x2(v[k + 2], v[k + 3]),
+                                                        pack_bf16x2(v[k + 4], v[k + 5]), pack_bf16x2(v[k + 6], v[k + 7]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -879,10 +1111,48 @@ static AttnParams to_params(const mmfm_attn_args* a) {
     }                                                                                             \
   } while (0)
 
+template <int D>
+static int launch_fwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
+  const int npad = (a->Sk + 15) / 16 * 16;
+  int tmem_cols = 32;
+  while (tmem_cols < npad + D) tmem_cols *= 2;
+  const TmaSwizzle sw = (D == 32) ? TMA_SW_64 : TMA_SW_128;
+  CUtensorMap tq, tk, tv;
+  const uint64_t width = (uint64_t)a->n_heads * D;
+  if (int rc = make_tmap_bf16_2d(&tq, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, 128, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npad, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npad, sw)) return rc;
+  const int smem = 1024 + (128 + 2 * 256) * D * 2;
+  const bool drop = a->drop_p.thresh != 0u;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[drop]) {
+    if (drop) MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[drop] = true;
+  }
+  dim3 grid((a->Sq + 127) / 128, a->n_heads, a->B);
+  if (drop) attn_fwd_tc_kernel<D, true><<<grid, 128, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
+  else attn_fwd_tc_kernel<D, false><<<grid, 128, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool g_attn_tc = true;   // MMFM_ATTN_TC=0 forces the mma.sync forward (A/B measurements)
+
 extern "C" int mmfm_attention_fwd(const mmfm_attn_args* a, void* stream) {
   if (int rc = check_common(a, "mmfm_attention_fwd")) return rc;
   const bool drop = a->drop_p.thresh != 0u, sep = a->mod_q != nullptr;
   const AttnParams p = to_params(a);
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("MMFM_ATTN_TC");
+    if (e && e[0] == '0') g_attn_tc = false;
+    env_read = true;
+  }
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+                      reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->o)) & 15) == 0;
+  if (g_attn_tc && !sep && a->Sk <= 256 && al16)
+    return a->d_head == 32 ? launch_fwd_tc<32>(a, p, (cudaStream_t)stream) : launch_fwd_tc<64>(a, p, (cudaStream_t)stream);
   dim3 grid((a->Sq + kTile - 1) / kTile, a->n_heads, a->B);
   cudaStream_t st = (cudaStream_t)stream;
   const int nkb = (a->Sk + kTile - 1) / kTile;
