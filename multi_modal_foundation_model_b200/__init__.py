@@ -4,3 +4,4 @@ from .config import DotDict, default_model_config, scaled_model_config  # noqa: 
 from .masker import Masker  # noqa: F401
 from .model import (DecoderEmbedding, EncoderEmbedding, MultiModal, MultiModalOutput, build_model,  # noqa: F401
                     convert)
+from .baselines import BaselineDecoder, BaselineEncoder  # noqa: F401,E402

@@ -810,11 +810,13 @@ __global__ void __launch_bounds__(kAttnThreads, D == 32 ? 3 : 2) attn_bwd_dkv_ke
 // The dropout field and the stored keep words are bit-identical to the flash kernel's (same Philox calls), so the
 // mma.sync backward kernels consume them unchanged.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kTcFwdThreads = 256;   // 2 column groups x 128 rows
+
 template <int D, bool DROP>
-__global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                          const __grid_constant__ CUtensorMap tmK,
-                                                          const __grid_constant__ CUtensorMap tmV, const AttnParams p,
-                                                          int npad, int tmem_cols) {
+__global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmK,
+                                                                    const __grid_constant__ CUtensorMap tmV,
+                                                                    const AttnParams p, int npad, int tmem_cols) {
   constexpr uint32_t kRowBytes = D * 2;                    // 64 (64B swizzle) or 128 (128B swizzle)
   constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;        // UMMA smem-descriptor swizzle code
   constexpr uint32_t kSbo = 8 * kRowBytes;                 // 8-row swizzle atom
@@ -822,10 +824,12 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   __shared__ __align__(8) uint64_t ld_bar, s_bar, o_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t s_colbits[8];
+  __shared__ float s_red[2][128];   // per column group: row max, later row sum
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base, sK = sQ + 128 * kRowBytes, sV = sK + 256 * kRowBytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int mode = p.mask_mode;
   const long long bh = (long long)(b * p.nh + h);
@@ -845,12 +849,10 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   }
   {
     const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
-    for (int w = warp; w < 8; w += 4) {
-      const int j = w * 32 + lane;
-      const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
-      const uint32_t m = __ballot_sync(0xffffffffu, v);
-      if (lane == 0) s_colbits[w] = m;
-    }
+    const int j = warp * 32 + lane;   // 8 warps -> 8 words
+    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
+    const uint32_t m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) s_colbits[warp] = m;
   }
   tc_fence_before();
   __syncthreads();
@@ -877,10 +879,11 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
     __syncwarp();
   }
 
-  // ---------------- softmax: thread = query row ----------------
-  const int i = q0 + tid;
+  // ---------------- softmax: thread = (query row, column group); group g owns the 32-column chunks c = g, g+2, .. ----
+  const int row = quad * 32 + lane;
+  const int i = q0 + row;
   const float sl2 = p.scale * kLog2e;
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
   const int nch = (npad + 31) >> 5;      // 32-column chunks
   const int nkb = (p.Sk + kTile - 1) / kTile;
   mbar_wait(&s_bar, 0);
@@ -897,22 +900,31 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
     return aw;
   };
 
+  // group g owns the 64-column blocks kb = g, g+2, ..  (chunks 2kb, 2kb+1): one set of Philox calls per block
+  const int nblk = (nch + 1) >> 1;
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < nch; ++c) {
-    uint32_t r[32];
-    tmem_ld32(t_row + 32u * c, r);
-    tmem_ld_wait();
-    const uint32_t aw = allowed_word(c);
-    if (aw == 0xFFFFFFFFu) {
+  for (int kb = grp; kb < nblk; kb += 2) {
+#pragma unroll 1
+    for (int c = 2 * kb; c < min(2 * kb + 2, nch); ++c) {
+      uint32_t r[32];
+      tmem_ld32(t_row + 32u * c, r);
+      tmem_ld_wait();
+      const uint32_t aw = allowed_word(c);
+      if (aw == 0xFFFFFFFFu) {
 #pragma unroll
-      for (int k = 0; k < 32; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
-    } else {
+        for (int k = 0; k < 32; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
+      } else {
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if ((aw >> k) & 1u) mx = fmaxf(mx, __uint_as_float(r[k]));
+        for (int k = 0; k < 32; ++k)
+          if ((aw >> k) & 1u) mx = fmaxf(mx, __uint_as_float(r[k]));
+      }
     }
   }
+  s_red[grp][row] = mx;
+  __syncthreads();
+  mx = fmaxf(s_red[0][row], s_red[1][row]);
+  __syncthreads();   // the buffer is reused for the row sums below
   const float base = (mx == -INFINITY) ? 0.f : mx * sl2;
   float l = 0.f;
   unsigned long long seed_p = 0ull;
@@ -922,55 +934,60 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
     thresh4 = p.drop_p.thresh * 0x01010101u;
   }
   const unsigned long long prow = (unsigned long long)bh * p.Sq + i;
-  uint32_t mw[4][4];   // keep byte-masks of the current 64-column block: [quad lane ql][word]
 #pragma unroll 1
-  for (int c = 0; c < nch; ++c) {
-    uint32_t r[32];
-    tmem_ld32(t_row + 32u * c, r);
-    tmem_ld_wait();
-    const uint32_t aw = allowed_word(c);
-    float pv[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      float e = fast_exp2(fmaf(__uint_as_float(r[k]), sl2, -base));
-      if (aw != 0xFFFFFFFFu && !((aw >> k) & 1u)) e = 0.f;
-      pv[k] = e;
-      l += e;
-    }
-    uint32_t pk[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) pk[t] = pack_bf16x2(pv[2 * t], pv[2 * t + 1]);
+  for (int kb = grp; kb < nblk; kb += 2) {
+    uint32_t mw[4][4];   // keep byte-masks of this block: [quad lane ql][word]
     if (DROP) {
-      const int kb = c >> 1, hf = c & 1;
-      if (hf == 0) {
 #pragma unroll
-        for (int ql = 0; ql < 4; ++ql) {
-          const uint4 w = pdrop_bytes(seed_p, p.drop_p.site, prow, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
-          mw[ql][0] = __vcmpgeu4(w.x, thresh4);
-          mw[ql][1] = __vcmpgeu4(w.y, thresh4);
-          mw[ql][2] = __vcmpgeu4(w.z, thresh4);
-          mw[ql][3] = __vcmpgeu4(w.w, thresh4);
-        }
-        if (i < p.Sq) {
-          const uint32_t lo = mask_bits16(mw[0]) | (mask_bits16(mw[1]) << 16);
-          const uint32_t hi = mask_bits16(mw[2]) | (mask_bits16(mw[3]) << 16);
-          *reinterpret_cast<uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + kb) * 4) = make_uint2(lo, hi);
-        }
+      for (int ql = 0; ql < 4; ++ql) {
+        const uint4 w = pdrop_bytes(seed_p, p.drop_p.site, prow, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
+        mw[ql][0] = __vcmpgeu4(w.x, thresh4);
+        mw[ql][1] = __vcmpgeu4(w.y, thresh4);
+        mw[ql][2] = __vcmpgeu4(w.z, thresh4);
+        mw[ql][3] = __vcmpgeu4(w.w, thresh4);
       }
-      // pair t covers columns 32c + 2t, +1: n-tile n = 4*hf + t/4, quad lane ql = t%4 -> bytes 2n, 2n+1 of call ql
+      if (i < p.Sq)
+        *reinterpret_cast<uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + kb) * 4) =
+            make_uint2(mask_bits16(mw[0]) | (mask_bits16(mw[1]) << 16), mask_bits16(mw[2]) | (mask_bits16(mw[3]) << 16));
+    }
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const int wsel = t >> 3;                                   // word (n >> 1) = 2*hf + t/8
-        const uint32_t wlo = mw[t & 3][wsel], whi = mw[t & 3][2 + wsel];
-        const uint32_t word = hf ? whi : wlo;
-        pk[t] &= ((t >> 2) & 1) ? __byte_perm(word, 0u, 0x3322u) : __byte_perm(word, 0u, 0x1100u);
+    for (int hf = 0; hf < 2; ++hf) {
+      const int c = 2 * kb + hf;
+      if (c < nch) {
+        uint32_t r[32];
+        tmem_ld32(t_row + 32u * c, r);
+        tmem_ld_wait();
+        const uint32_t aw = allowed_word(c);
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * t]), sl2, -base));
+          float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * t + 1]), sl2, -base));
+          if (aw != 0xFFFFFFFFu) {
+            if (!((aw >> (2 * t)) & 1u)) e0 = 0.f;
+            if (!((aw >> (2 * t + 1)) & 1u)) e1 = 0.f;
+          }
+          l += e0 + e1;
+          pk[t] = pack_bf16x2(e0, e1);
+        }
+        if (DROP) {
+          // pair t covers columns 32c + 2t, +1: n-tile n = 4*hf + t/4, quad lane ql = t%4 -> bytes 2n, 2n+1 of call ql:
+          // word 2*hf + t/8, half (t/4)&1
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const uint32_t word = mw[t & 3][2 * hf + (t >> 3)];
+            pk[t] &= ((t >> 2) & 1) ? __byte_perm(word, 0u, 0x3322u) : __byte_perm(word, 0u, 0x1100u);
+          }
+        }
+        tmem_st16(t_row + 32u * c, pk);   // in place: bf16 chunk c over the first 16 columns of fp32 chunk c
       }
     }
-    tmem_st16(t_row + 16u * c, pk);   // P chunk c aliases S columns [16c, 16c+16), all of them already consumed
   }
+  s_red[grp][row] = l;
   tmem_st_wait();
   tc_fence_before();
   __syncthreads();
+  l = s_red[0][row] + s_red[1][row];
 
   const uint32_t o_col = (uint32_t)npad;
   if (warp == 0) {
@@ -980,7 +997,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
       const int nks = npad >> 4;
       for (int kk = 0; kk < nks; ++kk) {
         const uint64_t db = make_smem_desc(sV + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout);
-        umma_bf16_ts(tmem_base + o_col, tmem_base + 8u * kk, db, idesc, kk > 0 ? 1u : 0u);
+        umma_bf16_ts(tmem_base + o_col, tmem_base + 32u * (kk >> 1) + 8u * (kk & 1), db, idesc, kk > 0 ? 1u : 0u);
       }
       umma_commit(&o_bar);
     }
@@ -989,37 +1006,33 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   mbar_wait(&o_bar, 0);
   tc_fence_after();
 
-  // ---------------- epilogue: O row -> scale, output dropout, store ----------------
+  // ---------------- epilogue: each group stores half of the O row ----------------
   float inv = l > 0.f ? 1.0f / l : 0.f;
-  if (i < p.Sq) p.lse[bh * p.Sq + i] = (l > 0.f) ? (base + log2f(l)) * kLn2 : -INFINITY;
+  if (grp == 0 && i < p.Sq) p.lse[bh * p.Sq + i] = (l > 0.f) ? (base + log2f(l)) * kLn2 : -INFINITY;
   if (DROP) inv *= p.drop_p.scale;
   const bool drop_o = p.drop_o.thresh != 0u;
   unsigned long long seed_o = 0ull;
   if (drop_o) seed_o = *p.drop_o.seed;
   const uint32_t gpr_o = (uint32_t)((p.nh * D + 15) >> 4);
 #pragma unroll
-  for (int c0 = 0; c0 < D; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(t_row + o_col + (uint32_t)c0, r);
+  for (int c0 = 0; c0 < D / 2; c0 += 16) {
+    const int cc = grp * (D / 2) + c0;   // column inside the head
+    uint32_t r[16];
+    tmem_ld16(t_row + o_col + (uint32_t)cc, r);
     tmem_ld_wait();
     if (i < p.Sq) {
-      float v[32];
+      float v[16];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) * inv;
-      const int col = h * D + c0;
+      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]) * inv;
+      const int col = h * D + cc;
       if (drop_o) {
+        const uint4 w = drop_bytes16(seed_o, p.drop_o.site, (uint64_t)((long long)b * p.Sq + i), gpr_o, (uint32_t)(col >> 4));
 #pragma unroll
-        for (int g16 = 0; g16 < 2; ++g16) {
-          const uint4 w = drop_bytes16(seed_o, p.drop_o.site, (uint64_t)((long long)b * p.Sq + i), gpr_o,
-                                       (uint32_t)((col + 16 * g16) >> 4));
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            v[16 * g16 + k] = drop_byte(w, k) < p.drop_o.thresh ? 0.f : v[16 * g16 + k] * p.drop_o.scale;
-        }
+        for (int k = 0; k < 16; ++k) v[k] = drop_byte(w, k) < p.drop_o.thresh ? 0.f : v[k] * p.drop_o.scale;
       }
       bf16* dst = p.o + ((long long)b * p.Sq + i) * p.ldo + col;
 #pragma unroll
-      for (int k = 0; k < 32; k += 8)
+      for (int k = 0; k < 16; k += 8)
         *reinterpret_cast<uint4*>(dst + k) = make_uint4(pack_bf16x2(v[k], v[k + 1]), pack_bf16x2(v[k + 2], v[k + 3]),
                                                         pack_bf16x2(v[k + 4], v[k + 5]), pack_bf16x2(v[k + 6], v[k + 7]));
     }
@@ -1027,6 +1040,369 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, tcgen05 / TMEM variant (Sq, Sk <= 256 and 2*Npad + accumulators <= 512 TMEM columns).  Two kernels with the
+// forward's structure, one per orientation, so no atomics and no transposed fragments:
+//   dq  : CTA = (b, h, 128 queries).  S = Q K^T and dP = dO V^T land side by side in TMEM; 512 threads (row = TMEM lane,
+//         4 column groups) turn them into dS = P * (keep * dP - delta) and write it back IN PLACE as bf16 (chunk c of
+//         32 fp32 columns -> its own first 16 columns), which the next tcgen05.mma reads as its A operand:
+//         dQ = dS . K  (K tile re-used as MN-major B operand).
+//   dkv : CTA = (b, h, 128 keys).  S^T = K Q^T, dP^T = V dO^T; the threads (row = key) produce dS^T and P_drop^T in
+//         place; dK = dS^T . Q and dV = P_drop^T . dO re-use the Q / dO tiles as MN-major B operands.
+// lse / delta / keep bits come from the forward and the prep kernel exactly as in the mma.sync path.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTcBwdThreads = 512;
+
+template <int D, bool DROP>
+__global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npad) {
+  constexpr uint32_t kRowBytes = D * 2;
+  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;
+  constexpr uint32_t kSbo = 8 * kRowBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t ld_bar, m1_bar, m2_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_colbits[8];
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sdO = sQ + 128 * kRowBytes, sK = sdO + 128 * kRowBytes, sV = sK + 256 * kRowBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int mode = p.mask_mode;
+  const long long bh = (long long)(b * p.nh + h);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(&ld_bar, 1);
+    mbar_init(&m1_bar, 1);
+    mbar_init(&m2_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  if (warp >= 8) {
+    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
+    const int w = warp - 8;
+    const int j = w * 32 + lane;
+    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
+    const uint32_t m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) s_colbits[w] = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t dp_col = (uint32_t)npad, acc_col = 2u * (uint32_t)npad;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npad) * kRowBytes));
+      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
+      tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq + q0);
+      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
+      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
+      mbar_wait(&ld_bar, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem_base, make_smem_desc(sQ + k * 32, 16, kSbo, kLayout), make_smem_desc(sK + k * 32, 16, kSbo, kLayout),
+                  idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem_base + dp_col, make_smem_desc(sdO + k * 32, 16, kSbo, kLayout),
+                  make_smem_desc(sV + k * 32, 16, kSbo, kLayout), idesc, k > 0 ? 1u : 0u);
+      umma_commit(&m1_bar);
+    }
+    __syncwarp();
+  }
+
+  const int row = quad * 32 + lane;
+  const int i = q0 + row;
+  const float sl2 = p.scale * kLog2e;
+  const float dsc = DROP ? p.drop_p.scale : 1.0f;
+  const float lse2 = (i < p.Sq) ? p.lse[bh * p.Sq + i] * kLog2e : INFINITY;
+  const float dl = ((i < p.Sq) ? p.delta[bh * p.Sq + i] : 0.f) / dsc;
+  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int nch = (npad + 31) >> 5;
+  const int nkb = (p.Sk + kTile - 1) / kTile;
+  mbar_wait(&m1_bar, 0);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (int c = grp; c < nch; c += 4) {
+    uint32_t aw = s_colbits[c];
+    const int rel = i - 32 * c;
+    if (mode == MMFM_MASK_KEY_OR_DIAG) {
+      if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
+    } else if (mode == MMFM_MASK_CAUSAL) {
+      aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
+    }
+    uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+    if (DROP && i < p.Sq) {
+      const uint2 w2 = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
+      const int sh = 8 * (c & 1);
+      kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
+      kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
+    }
+    uint32_t outp[16];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t rs[16], rd[16];
+      tmem_ld16(t_row + 32u * c + 16u * hf, rs);
+      tmem_ld16(t_row + dp_col + 32u * c + 16u * hf, rd);
+      tmem_ld_wait();
+      float ds[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int kk = 16 * hf + k;                 // column inside the chunk
+        const bool ok = (aw >> kk) & 1u;
+        const float pe = fast_exp2(fmaf(__uint_as_float(rs[k]), sl2, -lse2));
+        float dpe = __uint_as_float(rd[k]);
+        if (DROP) {
+          // column jj = 32*(c&1) + kk of the 64-block: n = jj/8, ql = (jj%8)/2, e = jj%2 -> bit 2n+e (kw pre-shifted)
+          if (!((kw[(kk & 7) >> 1] >> (2 * (kk >> 3) + (kk & 1))) & 1u)) dpe = 0.f;
+        }
+        ds[k] = ok ? pe * (dpe - dl) : 0.f;   // masked columns may hold uninitialised TMEM bits: never multiply them
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) outp[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
+    }
+    tmem_st16(t_row + 32u * c, outp);   // in place: bf16 chunk c over the first half of fp32 chunk c
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+      const int nks = npad >> 4;
+      for (int kk = 0; kk < nks; ++kk) {
+        const uint64_t db = make_smem_desc(sK + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout);
+        umma_bf16_ts(tmem_base + acc_col, tmem_base + 32u * (kk >> 1) + 8u * (kk & 1), db, idesc, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(&m2_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&m2_bar, 0);
+  tc_fence_after();
+  if (16 * grp < D) {
+    uint32_t r[16];
+    tmem_ld16(t_row + acc_col + 16u * grp, r);
+    tmem_ld_wait();
+    if (i < p.Sq) {
+      const float fs = p.scale * dsc;
+      bf16* dst = p.dq + ((long long)b * p.Sq + i) * p.lddq + h * D + 16 * grp;
+#pragma unroll
+      for (int k = 0; k < 16; k += 8)
+        *reinterpret_cast<uint4*>(dst + k) =
+            make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+template <int D, bool DROP>
+__global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npq) {
+  constexpr uint32_t kRowBytes = D * 2;
+  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;
+  constexpr uint32_t kSbo = 8 * kRowBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t ld_bar, m1_bar, m2_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_lse[256];
+  __shared__ __align__(16) float s_dl[256];
+  __shared__ __align__(16) unsigned short s_keep[256][8];   // [query][2 key blocks of this tile][4 quad lanes]
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = smem_base, sV = sK + 128 * kRowBytes, sQ = sV + 128 * kRowBytes, sdO = sQ + 256 * kRowBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int mode = p.mask_mode;
+  const long long bh = (long long)(b * p.nh + h);
+  const int nkb = (p.Sk + kTile - 1) / kTile;
+  const float dsc = DROP ? p.drop_p.scale : 1.0f;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(&ld_bar, 1);
+    mbar_init(&m1_bar, 1);
+    mbar_init(&m2_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  if (tid < 256) {
+    const int qi = tid;
+    const bool ok = qi < p.Sq;
+    s_lse[qi] = ok ? p.lse[bh * p.Sq + qi] * kLog2e : INFINITY;
+    s_dl[qi] = ok ? p.delta[bh * p.Sq + qi] / dsc : 0.f;
+    if (DROP) {
+      const int kb0 = k0 / kTile;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        uint2 w2 = make_uint2(0u, 0u);
+        if (ok && kb0 + u < nkb) w2 = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + qi) * nkb + kb0 + u) * 4);
+        *reinterpret_cast<uint2*>(&s_keep[qi][4 * u]) = w2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t dp_col = (uint32_t)npq, acc_col = 2u * (uint32_t)npq;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npq) * kRowBytes));
+      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk + k0);
+      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk + k0);
+      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq);
+      tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq);
+      mbar_wait(&ld_bar, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npq, 0, 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem_base, make_smem_desc(sK + k * 32, 16, kSbo, kLayout), make_smem_desc(sQ + k * 32, 16, kSbo, kLayout),
+                  idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem_base + dp_col, make_smem_desc(sV + k * 32, 16, kSbo, kLayout),
+                  make_smem_desc(sdO + k * 32, 16, kSbo, kLayout), idesc, k > 0 ? 1u : 0u);
+      umma_commit(&m1_bar);
+    }
+    __syncwarp();
+  }
+
+  const int row = quad * 32 + lane;   // key row of the tile
+  const int j = k0 + row;
+  const bool rowvalid = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || p.key_valid[(long long)b * p.Sk + j] != 0);
+  const float sl2 = p.scale * kLog2e;
+  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int nch = (npq + 31) >> 5;
+  // keep-bit address of this key inside a query's 8-word row: word 4*(row/64) + (row%8)/2, bit 2*((row%64)/8) + row%2
+  const int kword = 4 * (row >> 6) + ((row & 7) >> 1);
+  const int kbit = 2 * ((row & 63) >> 3) + (row & 1);
+  mbar_wait(&m1_bar, 0);
+  tc_fence_after();
+
+#pragma unroll 1
+  for (int c = grp; c < nch; c += 4) {
+    // allowed(query i = 32c + k, key j)
+    const int ncol = p.Sq - 32 * c;
+    uint32_t aw = ncol >= 32 ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));   // queries in range
+    const int rel = j - 32 * c;                                                        // column where i == j
+    if (mode == MMFM_MASK_CAUSAL) {
+      aw &= (rel <= 0) ? 0xFFFFFFFFu : (rel >= 32 ? 0u : ~((1u << rel) - 1u));          // i >= j
+      if (j >= p.Sk) aw = 0u;
+    } else {
+      const uint32_t inr = aw;
+      if (!rowvalid) aw = 0u;
+      if (mode == MMFM_MASK_KEY_OR_DIAG && rel >= 0 && rel < 32 && j < p.Sk) aw |= (1u << rel) & inr;
+    }
+    uint32_t outs[16], outp[16];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t rs[16], rd[16];
+      tmem_ld16(t_row + 32u * c + 16u * hf, rs);
+      tmem_ld16(t_row + dp_col + 32u * c + 16u * hf, rd);
+      tmem_ld_wait();
+      float ds[16], pd[16];
+#pragma unroll
+      for (int k4 = 0; k4 < 16; k4 += 4) {
+        const int qi = 32 * c + 16 * hf + k4;
+        const float4 l4 = *reinterpret_cast<const float4*>(&s_lse[qi]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&s_dl[qi]);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k4 + u, kk = 16 * hf + k;
+          const bool ok = (aw >> kk) & 1u;
+          const float pe = fast_exp2(fmaf(__uint_as_float(rs[k]), sl2, -lv[u]));
+          float dpe = __uint_as_float(rd[k]);
+          float pde = pe;
+          if (DROP) {
+            const uint32_t w = s_keep[qi + u][kword];
+            if (!((w >> kbit) & 1u)) { dpe = 0.f; pde = 0.f; }
+          }
+          ds[k] = ok ? pe * (dpe - dv[u]) : 0.f;   // masked columns may hold uninitialised TMEM bits
+          pd[k] = ok ? pde : 0.f;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        outs[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
+        outp[8 * hf + t] = pack_bf16x2(pd[2 * t], pd[2 * t + 1]);
+      }
+    }
+    tmem_st16(t_row + 32u * c, outs);
+    tmem_st16(t_row + dp_col + 32u * c, outp);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
+      const int nks = npq >> 4;
+      for (int kk = 0; kk < nks; ++kk) {
+        const uint32_t a_off = 32u * (kk >> 1) + 8u * (kk & 1);
+        umma_bf16_ts(tmem_base + acc_col, tmem_base + a_off,
+                     make_smem_desc(sQ + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc, kk > 0 ? 1u : 0u);
+        umma_bf16_ts(tmem_base + acc_col + D, tmem_base + dp_col + a_off,
+                     make_smem_desc(sdO + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(&m2_bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&m2_bar, 0);
+  tc_fence_after();
+  // 2*D accumulator columns (dK | dV) in 16-column pieces over the 4 thread groups
+  for (int piece = grp; piece < (2 * D) / 16; piece += 4) {
+    uint32_t r[16];
+    tmem_ld16(t_row + acc_col + 16u * piece, r);
+    tmem_ld_wait();
+    if (j < p.Sk) {
+      const bool is_dv = 16 * piece >= D;
+      const int col = 16 * piece - (is_dv ? D : 0);
+      const float fs = is_dv ? dsc : p.scale * dsc;
+      bf16* dst = (is_dv ? p.dv + ((long long)b * p.Sk + j) * p.lddv : p.dk + ((long long)b * p.Sk + j) * p.lddk) + h * D + col;
+#pragma unroll
+      for (int k = 0; k < 16; k += 8)
+        *reinterpret_cast<uint4*>(dst + k) =
+            make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
+                       pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 }  // namespace mmfm
@@ -1131,8 +1507,8 @@ static int launch_fwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStrea
     attr_set[drop] = true;
   }
   dim3 grid((a->Sq + 127) / 128, a->n_heads, a->B);
-  if (drop) attn_fwd_tc_kernel<D, true><<<grid, 128, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
-  else attn_fwd_tc_kernel<D, false><<<grid, 128, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
+  if (drop) attn_fwd_tc_kernel<D, true><<<grid, kTcFwdThreads, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
+  else attn_fwd_tc_kernel<D, false><<<grid, kTcFwdThreads, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1171,6 +1547,44 @@ static int launch_dkv(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t
   ATTN_DISPATCH(attn_bwd_dkv_kernel, grid, 6 * TileCfg<D>::kBytes + 4 * kTile * 4 + 2 * kTile * 4 * 2);
 }
 
+template <int D>
+static int launch_bwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
+  const int npk = (a->Sk + 15) / 16 * 16, npq = (a->Sq + 15) / 16 * 16;
+  const TmaSwizzle sw = (D == 32) ? TMA_SW_64 : TMA_SW_128;
+  const uint64_t width = (uint64_t)a->n_heads * D;
+  const bool drop = a->drop_p.thresh != 0u;
+  // dq: Q / dO tiles of 128 rows, K / V whole
+  CUtensorMap tq, tdo, tk, tv;
+  if (int rc = make_tmap_bf16_2d(&tq, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, 128, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tdo, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, 128, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npk, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npk, sw)) return rc;
+  const int smem = 1024 + (256 + 512) * D * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 gq((a->Sq + 127) / 128, a->n_heads, a->B);
+  if (drop) attn_bwd_dq_tc_kernel<D, true><<<gq, kTcBwdThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  else attn_bwd_dq_tc_kernel<D, false><<<gq, kTcBwdThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  // dkv: K / V tiles of 128 rows, Q / dO whole
+  CUtensorMap tq2, tdo2, tk2, tv2;
+  if (int rc = make_tmap_bf16_2d(&tq2, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, npq, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tdo2, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, npq, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tk2, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, 128, sw)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tv2, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, 128, sw)) return rc;
+  dim3 gk((a->Sk + 127) / 128, a->n_heads, a->B);
+  if (drop) attn_bwd_dkv_tc_kernel<D, true><<<gk, kTcBwdThreads, smem, st>>>(tq2, tdo2, tk2, tv2, p, npq);
+  else attn_bwd_dkv_tc_kernel<D, false><<<gk, kTcBwdThreads, smem, st>>>(tq2, tdo2, tk2, tv2, p, npq);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   if (int rc = check_common(a, "mmfm_attention_bwd")) return rc;
   MMFM_REQUIRE(a->d_o && a->delta && a->dq && a->dk && a->dv, "mmfm_attention_bwd: null gradient buffer");
@@ -1185,6 +1599,28 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   if (a->d_head == 32) attn_bwd_prep_kernel<32><<<pgrid, 256, 0, st>>>(p);
   else attn_bwd_prep_kernel<64><<<pgrid, 256, 0, st>>>(p);
   MMFM_CHECK_CUDA(cudaGetLastError());
+  {
+    static bool env_read = false;
+    if (!env_read) {
+      const char* e = getenv("MMFM_ATTN_TC");
+      if (e && e[0] == '0') g_attn_tc = false;
+      env_read = true;
+    }
+    const int npk = (a->Sk + 15) / 16 * 16, npq = (a->Sq + 15) / 16 * 16;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+                        reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->d_o) |
+                        reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) |
+                        reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0;
+    // TMEM budget: S and dP side by side plus the output accumulators
+    const bool fits = a->Sk <= 256 && a->Sq <= 256 && 2 * npk + a->d_head <= 512 && 2 * npq + 2 * a->d_head <= 512;
+    static int tc_bwd = -1;   // MMFM_ATTN_TC_BWD=1 selects the tcgen05 backward pair (see DESIGN.md 3.3 for the numbers)
+    if (tc_bwd < 0) {
+      const char* e = getenv("MMFM_ATTN_TC_BWD");
+      tc_bwd = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 32) return launch_bwd_tc<32>(a, p, st);
+    if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 64) return launch_bwd_tc<64>(a, p, st);
+  }
   if (int rc = launch_dq(a, p, st)) return rc;
   return launch_dkv(a, p, st);
 }
