@@ -842,6 +842,12 @@ __global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid
     mbar_init(&s_bar, 1);
     mbar_init(&o_bar, 1);
     fence_mbar_init();
+    // the operand tiles are requested before this CTA owns any tensor memory: a CTA that is resident but still
+    // waiting for TMEM columns already has its loads in flight, which hides their latency behind its predecessor
+    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((128 + 2 * npad) * kRowBytes));
+    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
+    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
+    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
   }
   if (warp == 1) {
     tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
@@ -861,10 +867,6 @@ __global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((128 + 2 * npad) * kRowBytes));
-      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
-      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
-      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
       mbar_wait(&ld_bar, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
@@ -1014,16 +1016,21 @@ __global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid
   unsigned long long seed_o = 0ull;
   if (drop_o) seed_o = *p.drop_o.seed;
   const uint32_t gpr_o = (uint32_t)((p.nh * D + 15) >> 4);
+  // pull this thread's part of the O row out of tensor memory, release the columns for the next CTA, then store
+  uint32_t r[D / 32][16];
 #pragma unroll
-  for (int c0 = 0; c0 < D / 2; c0 += 16) {
-    const int cc = grp * (D / 2) + c0;   // column inside the head
-    uint32_t r[16];
-    tmem_ld16(t_row + o_col + (uint32_t)cc, r);
-    tmem_ld_wait();
-    if (i < p.Sq) {
+  for (int u = 0; u < D / 32; ++u) tmem_ld16(t_row + o_col + (uint32_t)(grp * (D / 2) + 16 * u), r[u]);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (i < p.Sq) {
+#pragma unroll
+    for (int u = 0; u < D / 32; ++u) {
+      const int cc = grp * (D / 2) + 16 * u;   // column inside the head
       float v[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]) * inv;
+      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[u][k]) * inv;
       const int col = h * D + cc;
       if (drop_o) {
         const uint4 w = drop_bytes16(seed_o, p.drop_o.site, (uint64_t)((long long)b * p.Sq + i), gpr_o, (uint32_t)(col >> 4));
@@ -1037,9 +1044,6 @@ __global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid
                                                         pack_bf16x2(v[k + 4], v[k + 5]), pack_bf16x2(v[k + 6], v[k + 7]));
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1081,6 +1085,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
     mbar_init(&m1_bar, 1);
     mbar_init(&m2_bar, 1);
     fence_mbar_init();
+    // loads first, tensor memory second (see the forward kernel)
+    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npad) * kRowBytes));
+    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
+    tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq + q0);
+    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
+    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
   }
   if (warp == 1) {
     tmem_alloc(&tmem_slot, 512u);
@@ -1102,11 +1112,6 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npad) * kRowBytes));
-      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
-      tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq + q0);
-      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
-      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
       mbar_wait(&ld_bar, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
@@ -1132,11 +1137,22 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
   const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
   const int nch = (npad + 31) >> 5;
   const int nkb = (p.Sk + kTile - 1) / kTile;
+  // keep words of this thread's (at most two) chunks, fetched while the loads / first MMAs are in flight
+  uint2 kpre[2] = {make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu)};
+  if (DROP && i < p.Sq) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = grp + 4 * u;
+      if (c < nch) kpre[u] = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
+    }
+  }
   mbar_wait(&m1_bar, 0);
   tc_fence_after();
 
-#pragma unroll 1
-  for (int c = grp; c < nch; c += 4) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int c = grp + 4 * u;
+    if (c >= nch) break;
     uint32_t aw = s_colbits[c];
     const int rel = i - 32 * c;
     if (mode == MMFM_MASK_KEY_OR_DIAG) {
@@ -1145,8 +1161,8 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
       aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
     }
     uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
-    if (DROP && i < p.Sq) {
-      const uint2 w2 = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
+    if (DROP) {
+      const uint2 w2 = kpre[u];
       const int sh = 8 * (c & 1);
       kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
       kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
@@ -1195,10 +1211,15 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
   }
   mbar_wait(&m2_bar, 0);
   tc_fence_after();
+  uint32_t r[16];
   if (16 * grp < D) {
-    uint32_t r[16];
     tmem_ld16(t_row + acc_col + 16u * grp, r);
     tmem_ld_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);   // columns go back before the global stores
+  if (16 * grp < D) {
     if (i < p.Sq) {
       const float fs = p.scale * dsc;
       bf16* dst = p.dq + ((long long)b * p.Sq + i) * p.lddq + h * D + 16 * grp;
@@ -1211,9 +1232,6 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
                        pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 template <int D, bool DROP>
@@ -1246,6 +1264,11 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
     mbar_init(&m1_bar, 1);
     mbar_init(&m2_bar, 1);
     fence_mbar_init();
+    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npq) * kRowBytes));
+    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk + k0);
+    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk + k0);
+    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq);
+    tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq);
   }
   if (warp == 1) {
     tmem_alloc(&tmem_slot, 512u);
@@ -1274,11 +1297,6 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npq) * kRowBytes));
-      tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk + k0);
-      tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk + k0);
-      tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq);
-      tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq);
       mbar_wait(&ld_bar, 0);
       tc_fence_after();
       const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npq, 0, 0);
@@ -1381,12 +1399,20 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
   }
   mbar_wait(&m2_bar, 0);
   tc_fence_after();
-  // 2*D accumulator columns (dK | dV) in 16-column pieces over the 4 thread groups
-  for (int piece = grp; piece < (2 * D) / 16; piece += 4) {
-    uint32_t r[16];
-    tmem_ld16(t_row + acc_col + 16u * piece, r);
-    tmem_ld_wait();
-    if (j < p.Sk) {
+  // 2*D accumulator columns (dK | dV) in 16-column pieces over the 4 thread groups; tensor memory is released
+  // before the global stores
+  constexpr int kPieces = (2 * D) / 16, kPer = kPieces / 4;
+  uint32_t r[kPer][16];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) tmem_ld16(t_row + acc_col + 16u * (grp + 4 * u), r[u]);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+  if (j < p.Sk) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int piece = grp + 4 * u;
       const bool is_dv = 16 * piece >= D;
       const int col = 16 * piece - (is_dv ? D : 0);
       const float fs = is_dv ? dsc : p.scale * dsc;
@@ -1394,15 +1420,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
 #pragma unroll
       for (int k = 0; k < 16; k += 8)
         *reinterpret_cast<uint4*>(dst + k) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
+            make_uint4(pack_bf16x2(__uint_as_float(r[u][k]) * fs, __uint_as_float(r[u][k + 1]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 2]) * fs, __uint_as_float(r[u][k + 3]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 4]) * fs, __uint_as_float(r[u][k + 5]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 6]) * fs, __uint_as_float(r[u][k + 7]) * fs));
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 }  // namespace mmfm
@@ -1613,10 +1636,10 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
                         reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0;
     // TMEM budget: S and dP side by side plus the output accumulators
     const bool fits = a->Sk <= 256 && a->Sq <= 256 && 2 * npk + a->d_head <= 512 && 2 * npq + 2 * a->d_head <= 512;
-    static int tc_bwd = -1;   // MMFM_ATTN_TC_BWD=1 selects the tcgen05 backward pair (see DESIGN.md 3.3 for the numbers)
+    static int tc_bwd = -1;   // MMFM_ATTN_TC_BWD=0 falls back to the mma.sync backward pair (A/B measurements)
     if (tc_bwd < 0) {
       const char* e = getenv("MMFM_ATTN_TC_BWD");
-      tc_bwd = (e && e[0] == '1') ? 1 : 0;
+      tc_bwd = (e && e[0] == '0') ? 0 : 1;
     }
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 32) return launch_bwd_tc<32>(a, p, st);
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 64) return launch_bwd_tc<64>(a, p, st);
