@@ -1149,10 +1149,19 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
   mbar_wait(&m1_bar, 0);
   tc_fence_after();
 
+  // items = (chunk u, half hf): the TMEM loads of item n+1 are issued before item n is computed, so their latency is
+  // hidden behind the exp / select / pack work (tcgen05.wait::ld covers every outstanding load of the thread)
+  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
+  uint32_t rs[2][16], rd[2][16];
+  if (nmine > 0) {
+    tmem_ld16(t_row + 32u * grp, rs[0]);
+    tmem_ld16(t_row + dp_col + 32u * grp, rd[0]);
+    tmem_ld_wait();
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int c = grp + 4 * u;
-    if (c >= nch) break;
+    if (u >= nmine) break;
     uint32_t aw = s_colbits[c];
     const int rel = i - 32 * c;
     if (mode == MMFM_MASK_KEY_OR_DIAG) {
@@ -1170,17 +1179,22 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
     uint32_t outp[16];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      uint32_t rs[16], rd[16];
-      tmem_ld16(t_row + 32u * c + 16u * hf, rs);
-      tmem_ld16(t_row + dp_col + 32u * c + 16u * hf, rd);
-      tmem_ld_wait();
+      const int cur = hf, nxt = hf ^ 1;
+      // prefetch the next item
+      if (hf == 0) {
+        tmem_ld16(t_row + 32u * c + 16u, rs[nxt]);
+        tmem_ld16(t_row + dp_col + 32u * c + 16u, rd[nxt]);
+      } else if (u + 1 < nmine) {
+        tmem_ld16(t_row + 32u * (c + 4), rs[nxt]);
+        tmem_ld16(t_row + dp_col + 32u * (c + 4), rd[nxt]);
+      }
       float ds[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int kk = 16 * hf + k;                 // column inside the chunk
         const bool ok = (aw >> kk) & 1u;
-        const float pe = fast_exp2(fmaf(__uint_as_float(rs[k]), sl2, -lse2));
-        float dpe = __uint_as_float(rd[k]);
+        const float pe = fast_exp2(fmaf(__uint_as_float(rs[cur][k]), sl2, -lse2));
+        float dpe = __uint_as_float(rd[cur][k]);
         if (DROP) {
           // column jj = 32*(c&1) + kk of the 64-block: n = jj/8, ql = (jj%8)/2, e = jj%2 -> bit 2n+e (kw pre-shifted)
           if (!((kw[(kk & 7) >> 1] >> (2 * (kk >> 3) + (kk & 1))) & 1u)) dpe = 0.f;
@@ -1189,6 +1203,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
       }
 #pragma unroll
       for (int t = 0; t < 8; ++t) outp[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
+      tmem_ld_wait();
     }
     tmem_st16(t_row + 32u * c, outp);   // in place: bf16 chunk c over the first half of fp32 chunk c
   }
@@ -1325,8 +1340,17 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
   mbar_wait(&m1_bar, 0);
   tc_fence_after();
 
-#pragma unroll 1
-  for (int c = grp; c < nch; c += 4) {
+  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
+  uint32_t rs[2][16], rd[2][16];
+  if (nmine > 0) {
+    tmem_ld16(t_row + 32u * grp, rs[0]);
+    tmem_ld16(t_row + dp_col + 32u * grp, rd[0]);
+    tmem_ld_wait();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int c = grp + 4 * u;
+    if (u >= nmine) break;
     // allowed(query i = 32c + k, key j)
     const int ncol = p.Sq - 32 * c;
     uint32_t aw = ncol >= 32 ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));   // queries in range
@@ -1342,10 +1366,14 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
     uint32_t outs[16], outp[16];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      uint32_t rs[16], rd[16];
-      tmem_ld16(t_row + 32u * c + 16u * hf, rs);
-      tmem_ld16(t_row + dp_col + 32u * c + 16u * hf, rd);
-      tmem_ld_wait();
+      const int cur = hf, nxt = hf ^ 1;
+      if (hf == 0) {   // prefetch the next item's TMEM columns (see the dq kernel)
+        tmem_ld16(t_row + 32u * c + 16u, rs[nxt]);
+        tmem_ld16(t_row + dp_col + 32u * c + 16u, rd[nxt]);
+      } else if (u + 1 < nmine) {
+        tmem_ld16(t_row + 32u * (c + 4), rs[nxt]);
+        tmem_ld16(t_row + dp_col + 32u * (c + 4), rd[nxt]);
+      }
       float ds[16], pd[16];
 #pragma unroll
       for (int k4 = 0; k4 < 16; k4 += 4) {
@@ -1354,17 +1382,17 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
         const float4 d4 = *reinterpret_cast<const float4*>(&s_dl[qi]);
         const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int k = k4 + u, kk = 16 * hf + k;
+        for (int uu = 0; uu < 4; ++uu) {
+          const int k = k4 + uu, kk = 16 * hf + k;
           const bool ok = (aw >> kk) & 1u;
-          const float pe = fast_exp2(fmaf(__uint_as_float(rs[k]), sl2, -lv[u]));
-          float dpe = __uint_as_float(rd[k]);
+          const float pe = fast_exp2(fmaf(__uint_as_float(rs[cur][k]), sl2, -lv[uu]));
+          float dpe = __uint_as_float(rd[cur][k]);
           float pde = pe;
           if (DROP) {
-            const uint32_t w = s_keep[qi + u][kword];
+            const uint32_t w = s_keep[qi + uu][kword];
             if (!((w >> kbit) & 1u)) { dpe = 0.f; pde = 0.f; }
           }
-          ds[k] = ok ? pe * (dpe - dv[u]) : 0.f;   // masked columns may hold uninitialised TMEM bits
+          ds[k] = ok ? pe * (dpe - dv[uu]) : 0.f;   // masked columns may hold uninitialised TMEM bits
           pd[k] = ok ? pde : 0.f;
         }
       }
@@ -1373,6 +1401,7 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
         outs[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
         outp[8 * hf + t] = pack_bf16x2(pd[2 * t], pd[2 * t + 1]);
       }
+      tmem_ld_wait();
     }
     tmem_st16(t_row + 32u * c, outs);
     tmem_st16(t_row + dp_col + 32u * c, outp);
