@@ -1457,6 +1457,336 @@ __global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// backward, fused tcgen05 variant (d_head = 32, Sq, Sk <= 256): ONE CTA per (batch, head) computes dQ, dK and dV, so
+// every score element goes through the softmax / dropout / dS arithmetic once instead of once per orientation.
+// Per 128-query tile:
+//   MMA  S  = Q K^T                       -> TMEM [0, Npad)
+//   A    thread = (query row, column group): p = exp2(s*scale - lse) under the mask; P_drop (bf16) -> smem slabs;
+//        p stays in registers as packed bf16
+//   MMA  dP = dO V^T                      -> TMEM [0, Npad) (S is dead);   dV += P_drop^T dO   (A = slabs read MN-major)
+//   B    dS = p * (keep * dP - delta)     -> smem slabs
+//   MMA  dQ = dS K (A = slabs read K-major);  dK += dS^T Q (same slabs read MN-major)
+// The slabs are the canonical 128-byte-swizzled layout ([128 query rows] x [64 keys] per slab), written with 16-byte
+// stores from registers, so one copy of dS serves both the dQ (K-major A) and the dK (MN-major A) products.  dK / dV
+// accumulate in TMEM across the query tiles and are stored once at the end.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 512;
+constexpr uint32_t kSlabBytes = 128 * 128;   // 128 query rows x 64 keys (bf16)
+
+MMFM_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_fused_tc_kernel(
+    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npad) {
+  constexpr int D = 32;
+  constexpr uint32_t kRowBytes = 64, kSbo64 = 512;   // operand tiles: [rows][32 bf16], 64-byte swizzle
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t ld_kv_bar, ld_q_bar, s_bar, dp_bar, mm_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t s_colbits[8];
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = smem_base, sV = sK + 256 * kRowBytes, sQ = sV + 256 * kRowBytes, sdO = sQ + 128 * kRowBytes;
+  const uint32_t sdS = sdO + 128 * kRowBytes, sPd = sdS + 4 * kSlabBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, grp = warp >> 2;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int mode = p.mask_mode;
+  const long long bh = (long long)(b * p.nh + h);
+  const int nqt = (p.Sq + 127) >> 7;
+  const int nkt = (npad + 127) >> 7;   // 128-key M tiles of dK / dV
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(&ld_kv_bar, 1);
+    mbar_init(&ld_q_bar, 1);
+    mbar_init(&s_bar, 1);
+    mbar_init(&dp_bar, 1);
+    mbar_init(&mm_bar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&ld_kv_bar, (uint32_t)(2 * npad * kRowBytes));
+    tma_load_2d_addr(sK, &tmK, &ld_kv_bar, h * D, b * p.Sk);
+    tma_load_2d_addr(sV, &tmV, &ld_kv_bar, h * D, b * p.Sk);
+    mbar_arrive_expect_tx(&ld_q_bar, (uint32_t)(256 * kRowBytes));
+    tma_load_2d_addr(sQ, &tmQ, &ld_q_bar, h * D, b * p.Sq);
+    tma_load_2d_addr(sdO, &tmdO, &ld_q_bar, h * D, b * p.Sq);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, 512u);
+    tmem_relinquish();
+  }
+  if (warp >= 8) {
+    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
+    const int w = warp - 8;
+    const int j = w * 32 + lane;
+    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
+    const uint32_t m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) s_colbits[w] = m;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t dq_col = (uint32_t)npad, dk_col = dq_col + 32u, dv_col = dk_col + 64u;
+
+  const int row = quad * 32 + lane;
+  const float sl2 = p.scale * kLog2e;
+  const float dsc = DROP ? p.drop_p.scale : 1.0f;
+  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int nch = (npad + 31) >> 5;
+  const int nkb = (p.Sk + kTile - 1) / kTile;
+  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
+  const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)npad, 0, 0);   // S / dP: both operands K-major
+  const uint32_t idesc_q = make_idesc_bf16(128, D, 0, 1);                // dQ: A K-major (slabs), B MN-major (K tile)
+  const uint32_t idesc_t = make_idesc_bf16(128, D, 1, 1);                // dK / dV: A MN-major (slabs), B MN-major
+
+#pragma unroll 1
+  for (int qt = 0; qt < nqt; ++qt) {
+    const uint32_t par = (uint32_t)(qt & 1);
+    const int q0 = qt * 128;
+    const int i = q0 + row;
+    if (warp == 0) {
+      if (elect_one()) {
+        if (qt == 0) mbar_wait(&ld_kv_bar, 0);
+        mbar_wait(&ld_q_bar, par);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tmem_base, make_smem_desc(sQ + k * 32, 16, kSbo64, 4), make_smem_desc(sK + k * 32, 16, kSbo64, 4),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_bar);
+      }
+      __syncwarp();
+    }
+    const float lse2 = (i < p.Sq) ? p.lse[bh * p.Sq + i] * kLog2e : INFINITY;
+    const float dl = ((i < p.Sq) ? p.delta[bh * p.Sq + i] : 0.f) / dsc;
+    uint2 kpre[2] = {make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu)};
+    if (DROP && i < p.Sq) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = grp + 4 * u;
+        if (c < nch) kpre[u] = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
+      }
+    }
+    uint32_t aws[2] = {0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = grp + 4 * u;
+      if (c < nch) {
+        uint32_t aw = s_colbits[c];
+        const int rel = i - 32 * c;
+        if (mode == MMFM_MASK_KEY_OR_DIAG) {
+          if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
+        } else if (mode == MMFM_MASK_CAUSAL) {
+          aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
+        }
+        aws[u] = aw;
+      }
+    }
+    mbar_wait(&s_bar, par);
+    tc_fence_after();
+
+    // ---------------- pass A: probabilities ----------------
+    uint32_t pk[2][16];   // p as packed bf16, kept for pass B
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u >= nmine) break;
+      const int c = grp + 4 * u;
+      const uint32_t aw = aws[u];
+      uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+      if (DROP) {
+        const uint2 w2 = kpre[u];
+        const int sh = 8 * (c & 1);
+        kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
+        kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t rs[16];
+        tmem_ld16(t_row + 32u * c + 16u * hf, rs);
+        tmem_ld_wait();
+        uint32_t pdk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int k0 = 16 * hf + 2 * t, k1 = k0 + 1;
+          float e0 = fast_exp2(fmaf(__uint_as_float(rs[2 * t]), sl2, -lse2));
+          float e1 = fast_exp2(fmaf(__uint_as_float(rs[2 * t + 1]), sl2, -lse2));
+          if (!((aw >> k0) & 1u)) e0 = 0.f;
+          if (!((aw >> k1) & 1u)) e1 = 0.f;
+          pk[u][8 * hf + t] = pack_bf16x2(e0, e1);
+          if (DROP) {
+            if (!((kw[(k0 & 7) >> 1] >> (2 * (k0 >> 3) + (k0 & 1))) & 1u)) e0 = 0.f;
+            if (!((kw[(k1 & 7) >> 1] >> (2 * (k1 >> 3) + (k1 & 1))) & 1u)) e1 = 0.f;
+          }
+          pdk[t] = pack_bf16x2(e0, e1);
+        }
+        // two 16-byte pieces (8 keys each) of this row into the P_drop slab
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const int j16 = (c & 1) * 4 + hf * 2 + q4;
+          const uint32_t addr = sPd + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
+          st_shared_v4(addr, pdk[4 * q4], pdk[4 * q4 + 1], pdk[4 * q4 + 2], pdk[4 * q4 + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        // dP = dO V^T over the dead S columns
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tmem_base, make_smem_desc(sdO + k * 32, 16, kSbo64, 4), make_smem_desc(sV + k * 32, 16, kSbo64, 4),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&dp_bar);
+        // dV[key tile mt] += P_drop^T[keys, queries] . dO[queries, d]
+        for (int mt = 0; mt < nkt; ++mt)
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + dv_col + 32u * mt,
+                      make_smem_desc(sPd + (uint32_t)(2 * mt) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
+                      make_smem_desc(sdO + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_t,
+                      (qt > 0 || kk > 0) ? 1u : 0u);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&dp_bar, par);
+    tc_fence_after();
+
+    // ---------------- pass B: dS ----------------
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u >= nmine) break;
+      const int c = grp + 4 * u;
+      const uint32_t aw = aws[u];
+      uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+      if (DROP) {
+        const uint2 w2 = kpre[u];
+        const int sh = 8 * (c & 1);
+        kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
+        kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t rd[16];
+        tmem_ld16(t_row + 32u * c + 16u * hf, rd);
+        tmem_ld_wait();
+        uint32_t dsk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int k0 = 16 * hf + 2 * t, k1 = k0 + 1;
+          const float2 pp = unpack_bf16x2(pk[u][8 * hf + t]);
+          float d0 = __uint_as_float(rd[2 * t]), d1 = __uint_as_float(rd[2 * t + 1]);
+          if (DROP) {
+            if (!((kw[(k0 & 7) >> 1] >> (2 * (k0 >> 3) + (k0 & 1))) & 1u)) d0 = 0.f;
+            if (!((kw[(k1 & 7) >> 1] >> (2 * (k1 >> 3) + (k1 & 1))) & 1u)) d1 = 0.f;
+          }
+          const float s0 = ((aw >> k0) & 1u) ? pp.x * (d0 - dl) : 0.f;
+          const float s1 = ((aw >> k1) & 1u) ? pp.y * (d1 - dl) : 0.f;
+          dsk[t] = pack_bf16x2(s0, s1);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+          const int j16 = (c & 1) * 4 + hf * 2 + q4;
+          const uint32_t addr = sdS + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
+          st_shared_v4(addr, dsk[4 * q4], dsk[4 * q4 + 1], dsk[4 * q4 + 2], dsk[4 * q4 + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        // dQ = dS . K
+        const int nks = npad >> 4;
+        for (int kk = 0; kk < nks; ++kk)
+          umma_bf16(tmem_base + dq_col,
+                    make_smem_desc(sdS + (uint32_t)(kk >> 2) * kSlabBytes + (uint32_t)(kk & 3) * 32u, 16, 1024, 2),
+                    make_smem_desc(sK + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_q, kk > 0 ? 1u : 0u);
+        // dK[key tile mt] += dS^T . Q
+        for (int mt = 0; mt < nkt; ++mt)
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tmem_base + dk_col + 32u * mt,
+                      make_smem_desc(sdS + (uint32_t)(2 * mt) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
+                      make_smem_desc(sQ + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_t,
+                      (qt > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&mm_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&mm_bar, par);
+    tc_fence_after();
+    // every MMA that reads the Q / dO tiles and the slabs has finished: fetch the next query tile
+    if (tid == 0 && qt + 1 < nqt) {
+      mbar_arrive_expect_tx(&ld_q_bar, (uint32_t)(256 * kRowBytes));
+      tma_load_2d_addr(sQ, &tmQ, &ld_q_bar, h * D, b * p.Sq + q0 + 128);
+      tma_load_2d_addr(sdO, &tmdO, &ld_q_bar, h * D, b * p.Sq + q0 + 128);
+    }
+    if (grp < 2) {
+      uint32_t r[16];
+      tmem_ld16(t_row + dq_col + 16u * grp, r);
+      tmem_ld_wait();
+      if (i < p.Sq) {
+        const float fs = p.scale * dsc;
+        bf16* dst = p.dq + ((long long)b * p.Sq + i) * p.lddq + h * D + 16 * grp;
+#pragma unroll
+        for (int k = 0; k < 16; k += 8)
+          *reinterpret_cast<uint4*>(dst + k) =
+              make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
+                         pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
+                         pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
+                         pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
+      }
+    }
+    tc_fence_before();   // the dQ columns are rewritten by the next tile's MMA (ordered by the barriers of pass A)
+  }
+
+  // ---------------- dK / dV: TMEM lane = key row of the tile ----------------
+  // pieces: (mt, which, half) -> 16 columns; 4 * nkt pieces over the 4 thread groups
+  uint32_t r[2][16];
+  int npiece = 0;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int piece = grp + 4 * u;          // mt = piece / 4, which = (piece / 2) & 1 (0 dK, 1 dV), half = piece & 1
+    if (piece < 4 * nkt) {
+      const int mt = piece >> 2, which = (piece >> 1) & 1, half = piece & 1;
+      tmem_ld16(t_row + (which ? dv_col : dk_col) + 32u * mt + 16u * half, r[u]);
+      npiece = u + 1;
+    }
+  }
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (u >= npiece) break;
+    const int piece = grp + 4 * u;
+    const int mt = piece >> 2, which = (piece >> 1) & 1, half = piece & 1;
+    const int j = mt * 128 + row;
+    if (j < p.Sk) {
+      const float fs = which ? dsc : p.scale * dsc;
+      bf16* dst = (which ? p.dv + ((long long)b * p.Sk + j) * p.lddv : p.dk + ((long long)b * p.Sk + j) * p.lddk) + h * D + 16 * half;
+#pragma unroll
+      for (int k = 0; k < 16; k += 8)
+        *reinterpret_cast<uint4*>(dst + k) =
+            make_uint4(pack_bf16x2(__uint_as_float(r[u][k]) * fs, __uint_as_float(r[u][k + 1]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 2]) * fs, __uint_as_float(r[u][k + 3]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 4]) * fs, __uint_as_float(r[u][k + 5]) * fs),
+                       pack_bf16x2(__uint_as_float(r[u][k + 6]) * fs, __uint_as_float(r[u][k + 7]) * fs));
+    }
+  }
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1637,6 +1967,30 @@ static int launch_bwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStrea
   return 0;
 }
 
+static int launch_bwd_fused_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
+  constexpr int D = 32;
+  const int npk = (a->Sk + 15) / 16 * 16;
+  const uint64_t width = (uint64_t)a->n_heads * D;
+  const bool drop = a->drop_p.thresh != 0u;
+  CUtensorMap tq, tdo, tk, tv;
+  if (int rc = make_tmap_bf16_2d(&tq, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, 128, TMA_SW_64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tdo, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, 128, TMA_SW_64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npk, TMA_SW_64)) return rc;
+  if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npk, TMA_SW_64)) return rc;
+  const int smem = 1024 + (512 + 256) * 64 + 8 * 128 * 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(a->n_heads, a->B);
+  if (drop) attn_bwd_fused_tc_kernel<true><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  else attn_bwd_fused_tc_kernel<false><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   if (int rc = check_common(a, "mmfm_attention_bwd")) return rc;
   MMFM_REQUIRE(a->d_o && a->delta && a->dq && a->dk && a->dv, "mmfm_attention_bwd: null gradient buffer");
@@ -1670,6 +2024,13 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
       const char* e = getenv("MMFM_ATTN_TC_BWD");
       tc_bwd = (e && e[0] == '0') ? 0 : 1;
     }
+    static int fused = -1;    // MMFM_ATTN_FUSED_BWD=0 keeps the two-kernel tcgen05 backward
+    if (fused < 0) {
+      const char* e = getenv("MMFM_ATTN_FUSED_BWD");
+      fused = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (tc_bwd && fused && a->mod_q == nullptr && al16 && a->d_head == 32 && a->Sq <= 256 && a->Sk <= 256)
+      return launch_bwd_fused_tc(a, p, st);
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 32) return launch_bwd_tc<32>(a, p, st);
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 64) return launch_bwd_tc<64>(a, p, st);
   }
