@@ -38,20 +38,87 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="trials per GPU per step")
-    ap.add_argument("--neurons", type=int, default=668)
+    ap.add_argument("--workload", default="default", choices=["default", "scaled"],
+                    help="default = BASELINE configs[1] (the metric's config); scaled = configs[4] (24+24 layers, "
+                         "H 1024, 200 bins, spikes + 4 behaviour streams) -- an extra profile line, not the headline")
+    ap.add_argument("--batch", type=int, default=None, help="trials per GPU per step (256 default / 16 scaled)")
+    ap.add_argument("--neurons", type=int, default=None, help="spike channels (668 default / 1024 scaled)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="trials per step of the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity configuration)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    scaled = a.workload == "scaled"
+    if a.batch is None:
+        a.batch = 16 if scaled else 256
+    if a.neurons is None:
+        a.neurons = 1024 if scaled else 668
+    if scaled:
+        a.cpu_batch = 1
+    return a
+
+
+class Workload:
+    """Model / data shape of a bench run."""
+
+    def __init__(self, a):
+        from multi_modal_foundation_model_b200.config import default_model_config, scaled_model_config
+        self.scaled = a.workload == "scaled"
+        self.neurons = a.neurons
+        if self.scaled:
+            self.cfg = scaled_model_config()
+            self.mods = ["ap", "beh0", "beh1", "beh2", "beh3"]
+            self.extra = {m: 1 for m in self.mods[1:]}
+            self.n_beh, self.T = 4, 200
+            self.chan = [a.neurons, 1, 1, 1, 1]
+            self.desc = ("configs[4]: scaled variant, 24+24 layers, d_model 1024, 16 heads (d_head 64), MLP 2048, 200 "
+                         "time bins, ap spikes + 4 single-channel behaviour streams (S = 1000 tokens per trial)")
+        else:
+            self.cfg = default_model_config()
+            self.mods = ["ap", "behavior"]
+            self.extra = None
+            self.n_beh, self.T = 2, 100
+            self.chan = [a.neurons, 2]
+            self.desc = ("configs[1]: multi-modal encoder/decoder (ap spikes + wheel speed + whisker motion energy), "
+                         "mm.yaml default model 5+5 layers H256 8 heads MLP512, single synthetic IBL-shaped session")
+        tr = self.cfg["encoder"]["transformer"]
+        self.H, self.I, self.Le = tr["hidden_size"], tr["inter_size"], tr["n_layers"]
+        self.Ld = self.cfg["decoder"]["transformer"]["n_layers"]
+        self.S = self.T * len(self.mods)
+
+    def build(self):
+        from multi_modal_foundation_model_b200.model import build_model
+        return build_model(self.neurons, self.n_beh, self.cfg, avail_mod=tuple(self.mods), extra_channels=self.extra)
+
+    def batch(self, B, step, pin=False):
+        from multi_modal_foundation_model_b200.synthetic import make_batch
+        return make_batch(B, self.neurons, self.n_beh, self.T, step=step, pin=pin)
+
+    def inputs_of(self, batch):
+        out = []
+        for k, m in enumerate(self.mods):
+            if m == "ap":
+                out.append((m, batch["spikes_data"]))
+            elif m == "behavior":
+                out.append((m, batch["target"]))
+            else:
+                out.append((m, batch["target"][:, :, k - 1:k].contiguous()))
+        return out
+
+    def flops_fwd_per_trial(self) -> float:
+        """SURVEY.md section 8d 'Algorithmic work per trial' (dense attention, 2 FLOPs per multiply-add)."""
+        T, S, H, I = self.T, self.S, self.H, self.I
+        f = sum(2 * (2 * T * C * 2 * C + 2 * T * 2 * C * H) + 2 * T * H * C for C in self.chan)
+        f += self.Le * (8 * S * H * H + 4 * S * S * H + 4 * S * H * I)
+        f += self.Ld * (16 * S * H * H + 8 * S * S * H + 4 * S * H * I)
+        return float(f + 2 * S * H * H)
 
 
 def workload_config(a, n_gpus):
+    w = Workload(a)
     return {
-        "workload": "configs[1]: multi-modal encoder/decoder (ap spikes + wheel speed + whisker motion energy), "
-                    "mm.yaml default model 5+5 layers H256 8 heads MLP512, single synthetic IBL-shaped session",
-        "neurons": a.neurons, "behaviors": 2, "time_bins": 100, "tokens_per_trial": 200,
+        "workload": w.desc,
+        "neurons": a.neurons, "behaviors": w.n_beh, "time_bins": w.T, "tokens_per_trial": w.S,
         "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus,
         "mode": "eval() (dropout off)" if a.eval_mode else "train() (dropout 0.2/0.4 + masker active)",
         "training_modes": "encoding/decoding/token_masking cycled",
@@ -71,27 +138,28 @@ def cpu_reference_rate(a, seconds: float, min_steps: int = 2, fixed_steps: int =
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = default_model_config()
+    wl = Workload(a)
+    cfg = wl.cfg
     torch.manual_seed(42)
-    model = build_model(a.neurons, 2, cfg)
+    model = wl.build()
     P = {k: v.detach() for k, v in model.state_dict().items()}
     for k in list(P):
         if k.startswith("decoder_embeddings.") and k.endswith("mod_emb.weight"):
             P[k] = P[k.replace("decoder_embeddings.", "encoder_embeddings.")]
-    spec = orc.OracleSpec.from_config(cfg, ["ap", "behavior"])
+    spec = orc.OracleSpec.from_config(cfg, wl.mods)
     B = a.cpu_batch
 
     def one(step):
-        batch = make_batch(B, a.neurons, 2, 100, step=step)
+        batch = wl.batch(B, step)
         attn = batch["time_attn_mask"]
         mode = MODES[step % 3]
         g = torch.Generator().manual_seed(step)
         ob = {}
-        for m, x in (("ap", batch["spikes_data"]), ("behavior", batch["target"])):
+        for m, x in wl.inputs_of(batch):
             if mode == "token_masking":
-                mk = torch.bernoulli(torch.full((B, 100), 0.3), generator=g).long()
+                mk = torch.bernoulli(torch.full((B, wl.T), 0.3), generator=g).long()
             else:
-                mk = torch.full((B, 100), 1 if (m == "ap") == (mode == "encoding") else 0, dtype=torch.int64)
+                mk = torch.full((B, wl.T), 1 if (m == "ap") == (mode == "encoding") else 0, dtype=torch.int64)
             ob[m] = dict(inputs=x, targets=x, attn_mask=attn, timestamp=batch["spikes_timestamps"], mask=mk & attn)
         t0 = time.perf_counter()
         # dropout_seed set: train() mode like the GPU arm (masks from the documented Philox stream)
@@ -210,9 +278,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    cfg = default_model_config()
+    wl = Workload(a)
     torch.manual_seed(42)
-    model = build_model(a.neurons, 2, cfg).to(dev)
+    model = wl.build().to(dev)
     model.train(not a.eval_mode)
     model.masker.stream = "fast"     # throughput mode: draw only the (B,T) field the model uses (masker.py docstring)
     eng = model.engine()
@@ -223,9 +291,9 @@ def main():
     B = a.batch
 
     # rank r's shard of every global batch: its own seeded trials (weak scaling: B per GPU)
-    host_batches = [make_batch(B, a.neurons, 2, 100, step=1000 * rank + i, pin=True) for i in range(3)]
+    host_batches = [wl.batch(B, 1000 * rank + i, pin=True) for i in range(3)]
     dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
-    dev_dicts = [make_mod_dict(dev_batches[i], ["ap", "behavior"], MODES[i], device=dev) for i in range(3)]
+    dev_dicts = [make_mod_dict(dev_batches[i], wl.mods, MODES[i], device=dev) for i in range(3)]
 
     def step_resident(i):
         md = {k: dict(v) for k, v in dev_dicts[i % 3].items()}
@@ -237,7 +305,7 @@ def main():
     def step_e2e(i):
         hb = host_batches[i % 3]
         db = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}   # H2D
-        md = make_mod_dict(db, ["ap", "behavior"], MODES[i % 3], device=dev)
+        md = make_mod_dict(db, wl.mods, MODES[i % 3], device=dev)
         out = model(md)
         out.loss.backward()
         model.zero_grad(set_to_none=True)
@@ -329,7 +397,7 @@ def main():
     if rank == 0:
         cfgj = workload_config(a, n_gpus)
         cfgj["l2_policy"] = "per-step working set (activations + saved tensors, several GB at B=256) >> 126 MB L2"
-        flops_step = 3 * 3.79e9 * B if a.neurons == 668 else None
+        flops_step = 3 * wl.flops_fwd_per_trial() * B
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -338,7 +406,8 @@ def main():
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
-            "step_tensor_frac": (flops_step / (ms / a.steps * 1e-3) / 1e12 / 1370.0) if flops_step else None,
+            "flops_per_trial_fwd_bwd": 3 * wl.flops_fwd_per_trial(),
+            "step_tensor_frac": flops_step / (ms / a.steps * 1e-3) / 1e12 / 1370.0,
         }
         print(json.dumps(line))
     if world > 1:

@@ -21,23 +21,11 @@
 //   bwd prep  delta = rowsum(dO * O), dO <- dO * output-dropout mask
 //   bwd dq    rows = queries, cols = keys : dQ += (P * (dP - delta)) K
 //   bwd dkv   rows = keys, cols = queries : dV += P_drop^T dO ; dK += dS^T Q
-#include "common.cuh"
-#include "host_util.h"
-#include "../../include/mmfm_b200.h"
+#include "attn_common.cuh"
 #include <stdlib.h>
 
 namespace mmfm {
 
-constexpr int kAttnThreads = 128;
-constexpr int kTile = 64;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-MMFM_DEVINL float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 MMFM_DEVINL void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -52,27 +40,6 @@ MMFM_DEVINL void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-struct AttnParams {
-  const bf16* q; long long ldq;
-  const bf16* k; long long ldk;
-  const bf16* v; long long ldv;
-  bf16* o; long long ldo;
-  float* lse;
-  const unsigned char* key_valid;
-  const short* mod_q;
-  const short* mod_k;
-  int B, nh, Sq, Sk;
-  int mask_mode;
-  float scale;
-  DropCfg drop_p, drop_o;
-  unsigned short* p_keep;
-  // backward
-  bf16* d_o; long long lddo;
-  float* delta;
-  bf16* dq; long long lddq;
-  bf16* dk; long long lddk;
-  bf16* dv; long long lddv;
-};
 
 template <int D>
 struct TileCfg {
@@ -244,12 +211,6 @@ MMFM_DEVINL uint32_t keep_bits16(const uint4& w, uint32_t thresh4) {
 MMFM_DEVINL uint32_t mask_bits16(const uint32_t (&m)[4]) {
   return (((m[0] & 0x01010101u) * 0x01020408u) >> 24) | ((((m[1] & 0x01010101u) * 0x01020408u) >> 24) << 4) |
          ((((m[2] & 0x01010101u) * 0x01020408u) >> 24) << 8) | ((((m[3] & 0x01010101u) * 0x01020408u) >> 24) << 12);
-}
-// 16 random bytes of the probability-dropout field: row = (b*nh+h)*Sq + i, 64-column block blk, quad lane ql
-MMFM_DEVINL uint4 pdrop_bytes(unsigned long long seed, uint32_t site, unsigned long long row, uint32_t nblk,
-                              uint32_t blk, uint32_t ql) {
-  const unsigned long long g = (row * nblk + blk) * 4ull + ql;
-  return philox4x32((uint32_t)g, (uint32_t)(g >> 32), site, 1u, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
 // Per-thread allowed bits (2 x 16) for the mixed path.  The thread owns rows (ra, ra+8) and the 16 columns
@@ -1909,6 +1870,12 @@ extern "C" int mmfm_attention_fwd(const mmfm_attn_args* a, void* stream) {
   }
   const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
                       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->o)) & 15) == 0;
+  static int pipe = -1;   // MMFM_ATTN_PIPE=0 falls back to the one-CTA-per-tile forward kernels (A/B measurements)
+  if (pipe < 0) {
+    const char* e = getenv("MMFM_ATTN_PIPE");
+    pipe = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_attn_tc && pipe && !sep && al16) return launch_attn_fwd_pipe(a, p, (cudaStream_t)stream);
   if (g_attn_tc && !sep && a->Sk <= 256 && al16)
     return a->d_head == 32 ? launch_fwd_tc<32>(a, p, (cudaStream_t)stream) : launch_fwd_tc<64>(a, p, (cudaStream_t)stream);
   dim3 grid((a->Sq + kTile - 1) / kTile, a->n_heads, a->B);

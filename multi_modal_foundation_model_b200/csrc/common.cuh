@@ -56,12 +56,27 @@ MMFM_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the box.
+// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the box.  try_wait suspends the
+// thread in hardware for a bounded time, so the loop polls rarely; the bound is an iteration count (no clock reads
+// in the loop: a role warp that mostly waits must not steal issue slots from the math warps of its scheduler).
 MMFM_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++n > (1u << 26)) {
+      printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// Same for role warps (TMA producer, MMA issuer) that wait for long stretches: back off between polls.
+MMFM_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++n > (1u << 25)) {
       printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, parity);
       __trap();

@@ -119,6 +119,50 @@ def test_step_matches_oracle(cfg_kw, N, B, pad, dropout):
     print("worst grad rel-L2:", worst)
 
 
+@pytest.mark.parametrize("T,H,heads,N", [
+    (40, 128, 4, 48),      # S = 200 tokens: single-tile tcgen05 attention, d_head 32
+    (100, 128, 2, 72),     # S = 500 tokens: streaming attention, d_head 64
+])
+def test_five_modalities_match_oracle(T, H, heads, N):
+    """BASELINE configs[4] shape at test size: ap + 4 single-channel behaviour streams (n_modality 5), T != 100."""
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    mods = ["ap", "beh0", "beh1", "beh2", "beh3"]
+    cfg = default_model_config(n_layers=2, hidden_size=H, n_heads=heads, inter_size=2 * H, n_modality=5, max_F=T)
+    torch.manual_seed(3)
+    model = build_model(N, 4, cfg, avail_mod=tuple(mods), extra_channels={m: 1 for m in mods[1:]})
+    W = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    B = 2
+    batch = make_batch(B, N, 4, T, step=7, pad_bins=T // 10)
+    xs = {"ap": batch["spikes_data"]}
+    for k in range(4):
+        xs[f"beh{k}"] = batch["target"][:, :, k:k + 1].contiguous()
+    g = torch.Generator().manual_seed(9)
+    masks = {m: (torch.rand(B, T, generator=g) < 0.3).long() for m in mods}
+    md = {}
+    for i, m in enumerate(mods):
+        md[m] = dict(inputs=xs[m].cuda(), targets=xs[m].cuda(), inputs_attn_mask=batch["time_attn_mask"].cuda(),
+                     inputs_timestamp=batch["spikes_timestamps"].cuda(), inputs_modality=torch.tensor(i, device="cuda"),
+                     masking_mode=None, eval_mask=masks[m].cuda()[:, :, None].contiguous(),
+                     inputs_regions=np.array([["CA1"] * N] * B))
+    out = model(md)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    spec = orc.OracleSpec.from_config(cfg, mods)
+    ob = {m: dict(inputs=xs[m], targets=xs[m], attn_mask=batch["time_attn_mask"], timestamp=batch["spikes_timestamps"],
+                  mask=masks[m] & batch["time_attn_mask"]) for m in mods}
+    ref, grads = orc.forward_backward(oracle_params(W), spec, ob)
+    assert abs(out.loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (out.loss.item(), ref.loss.item())
+    for m in mods:
+        assert int(out.mod_n_examples[m]) == int(ref.mod_n_examples[m])
+        err = (out.mod_preds[m].detach().cpu() - ref.mod_preds[m].detach()).abs().max().item()
+        assert err < PRED_ATOL, (m, err)
+    _check_grads(model, grads, "five modalities")
+
+
 def test_masker_path_and_grad_accumulation():
     """token_masking through the host Masker (eval_mask=None) + two backward passes accumulate like autograd."""
     from multi_modal_foundation_model_b200.model import build_model

@@ -1,4 +1,5 @@
-"""Micro-benchmark of the attention kernels at the default-model shape (B=256, 8 heads, S=200, d=32)."""
+"""Micro-benchmark of the attention kernels: attn_bench.py [B] [dropout 0/1] [heads] [d_head] [S]
+(default-model shape B=256, 8 heads, d=32, S=200; scaled config: 16 1 16 64 1000)."""
 import sys
 import torch
 sys.path.insert(0, '.')
@@ -6,7 +7,9 @@ from multi_modal_foundation_model_b200 import ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 drop_on = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
-nh, d, S = 8, 32, 200
+nh = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+d = int(sys.argv[4]) if len(sys.argv) > 4 else 32
+S = int(sys.argv[5]) if len(sys.argv) > 5 else 200
 H = nh * d
 dev = "cuda"
 qkv = torch.randn(B * S, 3 * H, device=dev).to(torch.bfloat16)
