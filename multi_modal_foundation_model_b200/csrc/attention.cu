@@ -2000,6 +2000,12 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
       return launch_bwd_fused_tc(a, p, st);
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 32) return launch_bwd_tc<32>(a, p, st);
     if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 64) return launch_bwd_tc<64>(a, p, st);
+    static int stream = -1;   // MMFM_ATTN_STREAM_BWD=0 keeps the mma.sync backward for long sequences
+    if (stream < 0) {
+      const char* e = getenv("MMFM_ATTN_STREAM_BWD");
+      stream = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (tc_bwd && stream && a->mod_q == nullptr && al16) return launch_attn_bwd_stream(a, p, st);
   }
   if (int rc = launch_dq(a, p, st)) return rc;
   return launch_dkv(a, p, st);

@@ -48,5 +48,7 @@ MMFM_DEVINL uint4 pdrop_bytes(unsigned long long seed, uint32_t site, unsigned l
 
 // attention_pipe.cu: persistent warp-specialised tcgen05 forward (any Sk; no modality-separation mask)
 int launch_attn_fwd_pipe(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
+// attention_bwd_stream.cu: tcgen05 backward pair for long sequences (runs after the prep kernel)
+int launch_attn_bwd_stream(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
 
 }  // namespace mmfm

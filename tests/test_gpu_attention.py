@@ -47,6 +47,10 @@ def _ref(q, k, v, allowed, nh, d, keep_p=None, keep_o=None):
     (2, 4, 64, 257, 257, 0, True, 20),
     (1, 16, 64, 1000, 1000, 1, False, 100),
     (2, 8, 32, 64, 200, 0, False, 72),
+    (2, 4, 32, 300, 300, 2, False, 0),        # long sequence, causal, d_head 32: streaming kernels
+    (1, 8, 32, 520, 520, 1, False, 40),
+    (2, 4, 64, 130, 330, 0, False, 50),       # Sq != Sk across several key blocks
+    (1, 4, 64, 330, 130, 1, False, 0),
 ])
 @pytest.mark.parametrize("dropout", [False, True])
 def test_attention_fwd_bwd(B, nh, d, Sq, Sk, mode, sep, pad, dropout):
