@@ -338,6 +338,23 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = B * n_gpus * a.steps / (ms / 1e3)
 
+    # second number of SURVEY section 8d: the same step with the optimizer (fused AdamW over the flat buffers) included
+    from multi_modal_foundation_model_b200.optim import AdamW
+    opt = AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, eps=1e-8)
+
+    def step_optim(i):
+        md = {k: dict(v) for k, v in dev_dicts[i % 3].items()}
+        out = model(md)
+        out.loss.backward()
+        opt.step()
+        model.zero_grad(set_to_none=True)
+        return out
+
+    for i in range(3):
+        step_optim(i)
+    ms_opt = timed(step_optim, a.steps)
+    value_opt = B * n_gpus * a.steps / (ms_opt / 1e3)
+
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, a.steps)
@@ -405,6 +422,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches,
+            "with_optimizer": {"value": value_opt, "unit": UNIT, "ms_per_step": ms_opt / a.steps,
+                               "what": "fwd + bwd + fused AdamW step (mmfm_adamw_step over the flat fp32 buffers)"},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
             "flops_per_trial_fwd_bwd": 3 * wl.flops_fwd_per_trial(),
             "step_tensor_frac": flops_step / (ms / a.steps * 1e-3) / 1e12 / 1370.0,

@@ -201,6 +201,13 @@ int mmfm_cast_bf16_multi(const mmfm_cast_item* items_dev, int n_items, int total
  * scalar loss, trainer/base.py:195 always passes 1) */
 int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
 
+/* ---- optimizer step (torch.optim.AdamW of train_multi_modal.py:197-202 over the flat
+ *      master-parameter / gradient buffers; runs right after backward, trainer/base.py:196-198) ------------------- */
+/* p, g, exp_avg, exp_avg_sq: n fp32 elements each (16-byte aligned).  step >= 1 is the 1-based update count used for
+ * the bias corrections.  Decoupled weight decay, no amsgrad, maximize = false. */
+int mmfm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, long long step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 //   smallc_*             encoder_embeddings.py:50-61 and decoder_embeddings.py:105-107 for C <= 8 (behaviour, C = 2)
 //   loss_fwd_bwd         mm.py:217-239 with nn.PoissonNLLLoss(log_input=True) (:80) and nn.MSELoss (:81)
 #include "common.cuh"
+#include <math.h>
 #include "host_util.h"
 #include "../../include/mmfm_b200.h"
 
@@ -517,6 +518,33 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* __restrict__ 
     x[i] *= s;
 }
 
+// Fused multi-tensor AdamW over the flat master-parameter / gradient buffers (torch.optim.AdamW semantics,
+// reference train_multi_modal.py:197-202): p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+// p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).  One pass, 28 bytes of traffic per parameter.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                     float* __restrict__ m, float* __restrict__ v, long long n,
+                                                     float lr, float beta1, float beta2, float eps, float wd,
+                                                     float inv_bc1, float inv_sqrt_bc2) {
+  const long long n4 = n >> 2;
+  const float decay = 1.0f - lr * wd, step = lr * inv_bc1, c1 = 1.0f - beta1, c2 = 1.0f - beta2;
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    pp *= decay;
+    mm = fmaf(beta1, mm, c1 * gg);
+    vv = fmaf(beta2, vv, c2 * gg * gg);
+    pp -= step * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+  };
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -678,6 +706,19 @@ extern "C" int mmfm_scale_inplace(float* x, long long n, const float* scale_dev,
   MMFM_REQUIRE(x && scale_dev && n > 0, "mmfm_scale_inplace: bad arguments");
   MMFM_REQUIRE(((uintptr_t)x & 15) == 0, "mmfm_scale_inplace: buffer must be 16-byte aligned");
   scale_inplace_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, long long step, void* stream) {
+  MMFM_REQUIRE(p && g && exp_avg && exp_avg_sq && n > 0 && step >= 1, "mmfm_adamw_step: bad arguments");
+  MMFM_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+               "mmfm_adamw_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adamw_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                         weight_decay, (float)(1.0 / bc1),
+                                                                         (float)(1.0 / sqrt(bc2)));
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,7 @@ There is no PyTorch fallback: every arithmetic step is a kernel of libmmfm_b200.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -48,11 +49,29 @@ class ModSpec:
         self.small = channels <= SMALL_C
 
 
+_STORES = weakref.WeakSet()
+
+
+def embedding_groups(model):
+    """[(parameter-name prefix, encoder_embeddings, decoder_embeddings)]: one group for the reference's single-session
+    model, one per session for model.MultiSessionMultiModal (BASELINE configs[3])."""
+    sess = getattr(model, "session_embeddings", None)
+    if sess is None:
+        return [("", model.encoder_embeddings, model.decoder_embeddings)]
+    return [(f"session_embeddings.{k}.", v["encoder_embeddings"], v["decoder_embeddings"]) for k, v in sess.items()]
+
+
+def live_stores():
+    """Flat parameter stores of the engines alive in this process (optim.AdamW finds its parameters' owner here)."""
+    return list(_STORES)
+
+
 # ------------------------------------------------------------------------------------------------------------
 class ParamStore:
     """Flat fp32 master-parameter and gradient buffers + bf16 shadows."""
 
     def __init__(self, model, device):
+        _STORES.add(self)
         self.device = device
         named = dict(model.named_parameters(remove_duplicate=False))
         order = self._execution_reverse_order(model, named)
@@ -96,10 +115,11 @@ class ParamStore:
                 b = [f"{prefix}.key.bias", f"{prefix}.value.bias", f"{prefix}.query.bias"]
             return o + w + b
 
-        mods = list(model.decoder_embeddings.keys())
+        groups = embedding_groups(model)
         order: List[str] = []
-        for m in reversed(mods):
-            order += lin(f"decoder_embeddings.{m}.out")
+        for prefix, _, dec in reversed(groups):
+            for m in reversed(list(dec.keys())):
+                order += lin(f"{prefix}decoder_embeddings.{m}.out")
         order += lin("decoder_norm")
         for i in reversed(range(model.n_dec_layers)):
             p = f"decoder.{i}"
@@ -111,11 +131,12 @@ class ParamStore:
             p = f"encoder.{i}"
             order += lin(f"{p}.mlp.down_proj") + lin(f"{p}.mlp.up_proj") + lin(f"{p}.ln2")
             order += attn(f"{p}.attn", True) + lin(f"{p}.ln1")
-        for side in ("decoder_embeddings", "encoder_embeddings"):
-            for m in reversed(list(getattr(model, side).keys())):
-                p = f"{side}.{m}.embedder"
-                order += lin(f"{p}.projection") + lin(f"{p}.token_embed") + [f"{p}.pos_embed.weight",
-                                                                              f"{p}.mod_emb.weight"]
+        for prefix, enc, dec in reversed(groups):
+            for side, md in (("decoder_embeddings", dec), ("encoder_embeddings", enc)):
+                for m in reversed(list(md.keys())):
+                    p = f"{prefix}{side}.{m}.embedder"
+                    order += lin(f"{p}.projection") + lin(f"{p}.token_embed") + [f"{p}.pos_embed.weight",
+                                                                                  f"{p}.mod_emb.weight"]
         return [n for n in order if n in named]
 
     def view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
@@ -153,7 +174,7 @@ class ParamStore:
 class Shadows:
     """bf16 copies (natural and transposed) of the GEMM weights, refreshed by one multi-tensor cast launch."""
 
-    def __init__(self, store: ParamStore, model, mods: List[ModSpec]):
+    def __init__(self, store: ParamStore, model, sessions: Dict[Any, Tuple[str, List[ModSpec]]]):
         dev = store.device
         self.nat: Dict[str, torch.Tensor] = {}
         self.tr: Dict[str, torch.Tensor] = {}
@@ -201,14 +222,15 @@ class Shadows:
             add(f"{p}.cross_attn.out_proj", [f"{p}.cross_attn.out_proj.weight"])
             add(f"{p}.mlp.up_proj", [f"{p}.mlp.up_proj.weight"])
             add(f"{p}.mlp.down_proj", [f"{p}.mlp.down_proj.weight"])
-        for m in mods:
-            if m.small:
-                continue
-            for side in ("encoder_embeddings", "decoder_embeddings"):
-                p = f"{side}.{m.name}.embedder"
-                add(f"{p}.token_embed", [f"{p}.token_embed.weight"], want_t=False)
-                add(f"{p}.projection", [f"{p}.projection.weight"])
-            add(f"decoder_embeddings.{m.name}.out", [f"decoder_embeddings.{m.name}.out.weight"])
+        for prefix, mods in sessions.values():
+            for m in mods:
+                if m.small:
+                    continue
+                for side in ("encoder_embeddings", "decoder_embeddings"):
+                    p = f"{prefix}{side}.{m.name}.embedder"
+                    add(f"{p}.token_embed", [f"{p}.token_embed.weight"], want_t=False)
+                    add(f"{p}.projection", [f"{p}.projection.weight"])
+                add(f"{prefix}decoder_embeddings.{m.name}.out", [f"{prefix}decoder_embeddings.{m.name}.out.weight"])
         arr = (CastItem * len(items))(*items)
         self.items_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.n_items = len(items)
@@ -218,29 +240,62 @@ class Shadows:
         ops.cast_bf16_multi(self.items_dev, self.n_items, self.total_tiles)
 
 
+class Arena:
+    """Bump allocator over one device buffer.  Plans of different sessions (model.MultiSessionMultiModal) never run
+    concurrently, so their activation / saved-tensor buffers alias the same arena instead of multiplying the
+    footprint by the number of sessions; saved tensors of a plan stay valid until another plan's forward runs."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes: int, device):
+        self.buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        self.off = 0
+
+    def reset(self):
+        self.off = 0
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        n = (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.off + n > self.buf.numel():
+            raise MmfmError("activation arena exhausted (sized from the widest session)")
+        t = self.buf[self.off:self.off + nbytes]
+        self.off += n
+        return t
+
+
 # ------------------------------------------------------------------------------------------------------------
 class Plan:
     """All buffers + the recorded forward / backward launch lists for one (batch size, train/eval) shape."""
 
-    def __init__(self, eng: "Engine", B: int, training: bool):
+    def __init__(self, eng: "Engine", B: int, training: bool, session=None, arena: Optional[Arena] = None):
         self.eng, self.B, self.training = eng, B, training
+        self.arena_bytes = 0
+        if arena is not None:
+            arena.reset()
+        self.prefix, self.mods = eng.sessions[session]
         dev = eng.device
-        mods, T, H = eng.mods, eng.T, eng.H
+        mods, T, H = self.mods, eng.T, eng.H
         S = T * len(mods)
         R, BT = B * S, B * T
         self.S, self.R, self.BT = S, R, BT
 
         self._keep: List[Any] = []
 
-        def f32(*s):
-            t = torch.empty(*s, device=dev, dtype=torch.float32)
-            self._keep.append(t)      # recorded launches hold raw pointers: the plan owns every buffer
+        def raw(shape, dtype, esize):
+            n = int(np.prod(shape)) * esize
+            self.arena_bytes += (n + Arena.ALIGN - 1) // Arena.ALIGN * Arena.ALIGN
+            if arena is not None:
+                t = arena.take(n).view(dtype).view(*shape)
+            else:
+                t = torch.empty(*shape, device=dev, dtype=dtype)
+            self._keep.append(t)      # recorded launches hold raw pointers: the plan owns (or pins) every buffer
             return t
 
+        def f32(*s):
+            return raw(tuple(s), torch.float32, 4)
+
         def b16(r, c):
-            t = torch.empty(r, _pad(c), device=dev, dtype=bf16)
-            self._keep.append(t)
-            return t[:, :c]
+            return raw((r, _pad(c)), bf16, 2)[:, :c]
 
         def i64(*s):
             return torch.zeros(*s, device=dev, dtype=torch.int64)
@@ -350,7 +405,7 @@ class Plan:
     # ---------------------------------------------------------------------------------------------------
     def _build_forward(self, f32, b16):
         eng = self.eng
-        st, sh, mods = eng.store, eng.shadows, eng.mods
+        st, sh, mods = eng.store, eng.shadows, self.mods
         B, T, H, S, R, BT = self.B, eng.T, eng.H, self.S, self.R, self.BT
         self.stats: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.lse: Dict[str, torch.Tensor] = {}
@@ -370,7 +425,7 @@ class Plan:
         for side, sname, x0, p_emb in ((SIDE_ENC, "encoder_embeddings", self.xs[0], eng.hp["embed_dropout"]),
                                        (SIDE_DEC, "decoder_embeddings", self.ys[0], eng.hp["dec_embed_dropout"])):
             for k, m in enumerate(mods):
-                pre = f"{sname}.{m.name}.embedder"
+                pre = f"{self.prefix}{sname}.{m.name}.embedder"
                 off = k * T
                 pos = st.p(pre + ".pos_embed.weight") if st.has(pre + ".pos_embed.weight") else None
                 ops.embed_assemble(st.p(pre + ".mod_emb.weight")[m.index], pos, self.ts[m.name], self.emb[side], B=B,
@@ -461,7 +516,7 @@ class Plan:
         # ---- heads + fused masked loss / gradient (decoder_embeddings.py:95-109; mm.py:217-239) -------------
         self.dpreds: Dict[str, torch.Tensor] = {}
         for k, m in enumerate(mods):
-            pre = f"decoder_embeddings.{m.name}.out"
+            pre = f"{self.prefix}decoder_embeddings.{m.name}.out"
             ym = A["decoder_norm"][k * BT:(k + 1) * BT]
             pr = self.preds[m.name].view(BT, m.C)
             if m.small:
@@ -477,7 +532,7 @@ class Plan:
     # ---------------------------------------------------------------------------------------------------
     def _build_backward(self, f32, b16):
         eng = self.eng
-        st, sh, mods, hp = eng.store, eng.shadows, eng.mods, eng.hp
+        st, sh, mods, hp = eng.store, eng.shadows, self.mods, eng.hp
         B, T, H, S, R, BT = self.B, eng.T, eng.H, self.S, self.R, self.BT
         A = self.act
         G, Genc, Gctx = f32(R, H), f32(R, H), f32(R, H)       # fp32 residual-stream gradients
@@ -521,7 +576,7 @@ class Plan:
 
         # ---- heads (reverse order = gradient-bucket order) -------------------------------------------------
         for k, m in reversed(list(enumerate(mods))):
-            pre = f"decoder_embeddings.{m.name}.out"
+            pre = f"{self.prefix}decoder_embeddings.{m.name}.out"
             ym = A["decoder_norm"][k * BT:(k + 1) * BT]
             dym = ddec[k * BT:(k + 1) * BT]
             if m.small:
@@ -574,7 +629,7 @@ class Plan:
         for side, sname, Gs, G2, p_emb in ((SIDE_DEC, "decoder_embeddings", G, None, hp["dec_embed_dropout"]),
                                            (SIDE_ENC, "encoder_embeddings", Genc, Gctx, hp["embed_dropout"])):
             for k, m in reversed(list(enumerate(mods))):
-                pre = f"{sname}.{m.name}.embedder"
+                pre = f"{self.prefix}{sname}.{m.name}.embedder"
                 off = k * T
                 dpos = st.g(pre + ".pos_embed.weight") if st.has(pre + ".pos_embed.weight") else None
                 ops.embed_assemble_bwd(Gs, G2, self.ts[m.name], dpos, st.g(pre + ".mod_emb.weight")[m.index], B=B, T=T,
@@ -671,12 +726,19 @@ class Engine:
         if act not in ("softsign", "identity"):
             raise NotImplementedError(f"embedder act {act!r}: only 'softsign' (mm.yaml:33) and 'identity' are built")
         self.embed_act = ACT_SOFTSIGN if act == "softsign" else ACT_NONE
-        names = list(model.decoder_embeddings.keys())
-        if names != list(model.encoder_embeddings.keys()):
-            raise NotImplementedError("encoder and decoder must embed the same modalities in the same order")
-        self.mods = [ModSpec(n, model.mod_to_indx[n], model.encoder_embeddings[n].n_channel,
-                             model.loss_kind.get(n, "mse")) for n in names]
-        e0 = model.encoder_embeddings[names[0]].embedder
+        # one (prefix, modality list) per session; the reference's single-session model is the session None
+        self.sessions: Dict[Any, Tuple[str, List[ModSpec]]] = {}
+        groups = embedding_groups(model)
+        self.multi_session = getattr(model, "session_embeddings", None) is not None
+        for prefix, enc, dec in groups:
+            names = list(dec.keys())
+            if names != list(enc.keys()):
+                raise NotImplementedError("encoder and decoder must embed the same modalities in the same order")
+            key = prefix.split(".")[1] if self.multi_session else None
+            self.sessions[key] = (prefix, [ModSpec(n, model.mod_to_indx[n], enc[n].n_channel,
+                                                   model.loss_kind.get(n, "mse")) for n in names])
+        self.mods = next(iter(self.sessions.values()))[1]
+        e0 = groups[0][1][names[0]].embedder
         self.embed_scale = float(e0.scale)
         if self.embed_act == ACT_NONE and self.embed_scale != 1.0:
             raise NotImplementedError("identity embedder activation needs scale == 1")
@@ -687,8 +749,9 @@ class Engine:
                 raise NotImplementedError(f"head size {self.H // nh}: the attention kernels are built for 32 and 64")
         self.T: Optional[int] = None
         self.store = ParamStore(model, self.device)
-        self.shadows = Shadows(self.store, model, self.mods)
-        self.plans: Dict[Tuple[int, bool], Plan] = {}
+        self.shadows = Shadows(self.store, model, self.sessions)
+        self.plans: Dict[Tuple[int, bool, Any], Plan] = {}
+        self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.ddp = None          # set by parallel.DataParallel
         import os as _os
         self.use_graphs = _os.environ.get("MMFM_CUDA_GRAPHS", "1") != "0"
@@ -696,16 +759,27 @@ class Engine:
         self._grad_views = None
 
     # ---------------------------------------------------------------------------------------------------
-    def _plan(self, B: int, T: int, training: bool) -> Plan:
+    def _plan(self, B: int, T: int, training: bool, session=None) -> Plan:
         if self.T is None:
             self.T = T
         elif self.T != T:
             self.plans.clear()
+            self.arenas.clear()
             self.T = T
-        key = (B, training)
+        key = (B, training, session)
         pl = self.plans.get(key)
         if pl is None:
-            pl = Plan(self, B, training)
+            arena = None
+            if self.multi_session:
+                arena = self.arenas.get((B, training))
+                if arena is None:
+                    # size the shared arena from the widest session (buffers grow monotonically with the channels)
+                    widest = max(self.sessions, key=lambda k: sum(m.C for m in self.sessions[k][1]))
+                    probe = Plan(self, B, training, widest)
+                    nbytes = probe.arena_bytes + (1 << 20)
+                    del probe
+                    arena = self.arenas[(B, training)] = Arena(nbytes, self.device)
+            pl = Plan(self, B, training, session, arena)
             self.plans[key] = pl
         return pl
 
@@ -714,7 +788,15 @@ class Engine:
         model = self.model
         if not self.store.adopted():
             self.store.adopt()
-        names = [m.name for m in self.mods]
+        session = None
+        if self.multi_session:
+            # one session per batch (trainer/base.py:65); the batch's eid selects its embedders and heads
+            eid = next(iter(mod_dict.values())).get("eid")
+            session = model.session_key(eid)
+            if session not in self.sessions:
+                raise MmfmError(f"unknown session {eid!r}: the model holds {sorted(self.sessions)[:4]} ...")
+        mods = self.sessions[session][1]
+        names = [m.name for m in mods]
         if list(mod_dict.keys()) != names:
             raise MmfmError(f"mod_dict must hold exactly the modalities {names} in this order")
         d0 = mod_dict[names[0]]
@@ -722,8 +804,8 @@ class Engine:
             raise MmfmError("first modality must be (B,T,C)")
         B, T = d0["inputs"].shape[:2]
         training = bool(model.training)
-        pl = self._plan(B, T, training)
-        for m in self.mods:
+        pl = self._plan(B, T, training, session)
+        for m in mods:
             d = mod_dict[m.name]
             if d["inputs"].dim() == 2:                                   # mm.py:248-250
                 d["inputs"] = d["inputs"].unsqueeze(-1)
@@ -758,7 +840,7 @@ class Engine:
         out_loss, out_n, out_p, out_t = {}, {}, {}, {}
         mod_loss = pl.mod_loss.clone()
         nex = pl.nex.clone()
-        for k, m in enumerate(self.mods):
+        for k, m in enumerate(mods):
             d = mod_dict[m.name]
             out_loss[m.name] = mod_loss[k]
             out_n[m.name] = nex[k]

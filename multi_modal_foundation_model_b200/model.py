@@ -290,6 +290,50 @@ class MultiModal(nn.Module):
         return self.engine().step(mod_dict)
 
 
+class MultiSessionMultiModal(MultiModal):
+    """Multi-session pre-training (BASELINE.json configs[3]; SURVEY.md section 8d config 4 -- an extension, the
+    reference trains one session): ONE shared transformer, per-session ``EncoderEmbedding`` / ``DecoderEmbedding``
+    modules (token_embed, projection, pos_embed, mod_emb, out head -- the "stitching" layers, sized by that
+    session's neuron count) selected by the batch's ``eid`` (one session per batch, trainer/base.py:65).
+
+    ``state_dict`` keys: the shared layers keep the reference's names; session *k*'s embedders live under
+    ``session_embeddings.<key>.{encoder,decoder}_embeddings.<mod>...`` -- stripping that prefix gives exactly the
+    reference's single-session keys, which is how the parity test feeds the oracle."""
+
+    def __init__(self, session_channels: Dict[str, Dict[str, int]], avail_mod: List, config,
+                 share_modality_embeddings: bool = True, **kwargs):
+        first = next(iter(session_channels.values()))
+        enc0 = {m: EncoderEmbedding(n_channel=first[m], config=cfg_get(config, "encoder")) for m in avail_mod}
+        dec0 = {m: DecoderEmbedding(n_channel=first[m], output_channel=first[m], config=cfg_get(config, "decoder"))
+                for m in avail_mod}
+        super().__init__(enc0, dec0, avail_mod, config, share_modality_embeddings, **kwargs)
+        # the per-session modules replace the single pair of the base class
+        del self.encoder_embeddings, self.decoder_embeddings
+        self._session_keys: Dict[str, str] = {}
+        sess = {}
+        for k, (eid, chan) in enumerate(session_channels.items()):
+            key = f"s{k:03d}"
+            self._session_keys[str(eid)] = key
+            if k == 0:
+                enc, dec = enc0, dec0
+            else:
+                enc = {m: EncoderEmbedding(n_channel=chan[m], config=cfg_get(config, "encoder")) for m in avail_mod}
+                dec = {m: DecoderEmbedding(n_channel=chan[m], output_channel=chan[m],
+                                           config=cfg_get(config, "decoder")) for m in avail_mod}
+                if share_modality_embeddings:
+                    for m in avail_mod:
+                        dec[m].embedder.mod_emb = enc[m].embedder.mod_emb
+            sess[key] = nn.ModuleDict({"encoder_embeddings": nn.ModuleDict(enc),
+                                       "decoder_embeddings": nn.ModuleDict(dec)})
+        self.session_embeddings = nn.ModuleDict(sess)
+
+    def session_key(self, eid) -> Optional[str]:
+        return self._session_keys.get(str(eid))
+
+    def session_prefix(self, eid) -> str:
+        return f"session_embeddings.{self._session_keys[str(eid)]}."
+
+
 def build_model(n_neurons: int, n_behaviors: int, config, avail_mod=("ap", "behavior"), extra_channels=None,
                 **kwargs) -> MultiModal:
     """Mirror of train_multi_modal.py:160-189: per-modality embedders then the model."""

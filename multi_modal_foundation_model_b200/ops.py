@@ -176,6 +176,13 @@ def scale_inplace(x: torch.Tensor, scale_dev: torch.Tensor) -> None:
     _launch("mmfm_scale_inplace", x.data_ptr(), x.numel(), scale_dev.data_ptr())
 
 
+def adamw_step(p: torch.Tensor, g: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
+               beta1: float, beta2: float, eps: float, weight_decay: float, step: int) -> None:
+    n = p.numel()
+    _launch("mmfm_adamw_step", p.data_ptr(), g.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n, float(lr),
+            float(beta1), float(beta2), float(eps), float(weight_decay), int(step), meta={"bytes": 28.0 * n})
+
+
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, *, R: int, H: int, eps: float = 1e-5, modmajor_T: int = 0,
                   S: int = 0) -> None:
     _launch("mmfm_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),

@@ -190,3 +190,62 @@ def test_masker_path_and_grad_accumulation():
     with torch.no_grad():
         out3 = model(make_mod_dict(batch, ["ap", "behavior"], "decoding", device="cuda"))
     assert out3.loss.requires_grad is False and torch.isfinite(out3.loss)
+
+
+def test_multi_session_matches_oracle_per_session():
+    """BASELINE configs[3]: shared transformer + per-session embedders / heads selected by eid.  Every session's step
+    equals the single-session oracle run with that session's parameters (prefix stripped); the other sessions'
+    embedders receive exactly zero gradient; all sessions' plans share one activation arena."""
+    from multi_modal_foundation_model_b200.model import MultiSessionMultiModal
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    cfg = small_config()
+    chans = {"sess-a": {"ap": 40, "behavior": 2}, "sess-b": {"ap": 88, "behavior": 2}, "sess-c": {"ap": 56, "behavior": 2}}
+    torch.manual_seed(21)
+    model = MultiSessionMultiModal(chans, ["ap", "behavior"], cfg)
+    W = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    spec = orc.OracleSpec.from_config(cfg, ["ap", "behavior"])
+    B = 2
+    for step, (eid, ch) in enumerate(chans.items()):
+        N = ch["ap"]
+        batch = make_batch(B, N, 2, 100, step=step, pad_bins=5)
+        g = torch.Generator().manual_seed(step)
+        masks = {m: (torch.rand(B, 100, generator=g) < 0.3).long() for m in ("ap", "behavior")}
+        md = _mod_dict(batch["spikes_data"], batch["target"], batch["time_attn_mask"], batch["spikes_timestamps"], masks)
+        for d in md.values():
+            d["eid"] = eid
+        out = model(md)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        prefix = model.session_prefix(eid)
+        P = {}
+        for k, v in W.items():
+            if k.startswith("session_embeddings."):
+                if k.startswith(prefix):
+                    P[k[len(prefix):]] = v
+            else:
+                P[k] = v
+        ob = {m: dict(inputs=x, targets=x, attn_mask=batch["time_attn_mask"], timestamp=batch["spikes_timestamps"],
+                      mask=masks[m] & batch["time_attn_mask"])
+              for m, x in (("ap", batch["spikes_data"]), ("behavior", batch["target"]))}
+        ref, grads = orc.forward_backward(oracle_params(P), spec, ob)
+        assert abs(out.loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (eid, out.loss.item())
+        for n, p in model.named_parameters():
+            if n.startswith("session_embeddings."):
+                if not n.startswith(prefix):
+                    assert p.grad is None or float(p.grad.abs().max()) == 0.0, (eid, n)
+                    continue
+                g_ref = grads[n[len(prefix):]]
+            else:
+                g_ref = grads[n]
+            if g_ref.norm() < 1e-6:
+                continue
+            r, c = rel_l2(p.grad.cpu(), g_ref), cosine(p.grad.cpu(), g_ref)
+            assert r < GRAD_RL2 and c > GRAD_COS, f"{eid}: {n} rel-L2 {r:.4g} cosine {c:.6f}"
+        model.zero_grad(set_to_none=True)
+    eng = model.engine()
+    assert len(eng.plans) == 3 and len(eng.arenas) == 1
+    arena = next(iter(eng.arenas.values())).buf
+    lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel()
+    assert all(lo <= pl.xs[0].data_ptr() < hi for pl in eng.plans.values())   # residual streams alias one arena

@@ -116,3 +116,21 @@ def test_default_config_restates_mm_yaml():
             else:
                 assert b[k] == v, (path + k, b[k], v)
     walk(dict(cfg), ours)
+
+
+def test_multi_session_model_keys_and_pickle():
+    """configs[3] container: shared layers keep the reference's names, per-session embedders sit under a prefix that,
+    once stripped, gives the reference's single-session keys."""
+    import pickle
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import MultiSessionMultiModal, build_model
+    cfg = default_model_config(n_layers=1, hidden_size=64, n_heads=2, inter_size=128)
+    m = MultiSessionMultiModal({"e1": {"ap": 24, "behavior": 2}, "e2": {"ap": 40, "behavior": 2}}, ["ap", "behavior"], cfg)
+    single = set(build_model(40, 2, cfg).state_dict().keys())
+    pre = m.session_prefix("e2")
+    keys = set(m.state_dict().keys())
+    stripped = {k[len(pre):] if k.startswith(pre) else k for k in keys if not k.startswith("session_embeddings.") or k.startswith(pre)}
+    assert stripped == single
+    assert m.state_dict()[pre + "encoder_embeddings.ap.embedder.token_embed.weight"].shape == (80, 40)
+    m2 = pickle.loads(pickle.dumps(m))
+    assert m2.session_key("e1") == "s000" and m2.session_key("nope") is None
