@@ -38,9 +38,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="default", choices=["default", "scaled"],
+    ap.add_argument("--workload", default="default", choices=["default", "scaled", "multisession"],
                     help="default = BASELINE configs[1] (the metric's config); scaled = configs[4] (24+24 layers, "
-                         "H 1024, 200 bins, spikes + 4 behaviour streams) -- an extra profile line, not the headline")
+                         "H 1024, 200 bins, spikes + 4 behaviour streams); multisession = configs[3] (32 sessions with "
+                         "256-1024 neurons, per-session embedders) -- extra profile lines, not the headline")
+    ap.add_argument("--sessions", type=int, default=32)
     ap.add_argument("--batch", type=int, default=None, help="trials per GPU per step (256 default / 16 scaled)")
     ap.add_argument("--neurons", type=int, default=None, help="spike channels (668 default / 1024 scaled)")
     ap.add_argument("--cpu-batch", type=int, default=16, help="trials per step of the CPU sample")
@@ -64,8 +66,23 @@ class Workload:
     def __init__(self, a):
         from multi_modal_foundation_model_b200.config import default_model_config, scaled_model_config
         self.scaled = a.workload == "scaled"
+        self.multi = a.workload == "multisession"
         self.neurons = a.neurons
-        if self.scaled:
+        self.session_neurons = None
+        if self.multi:
+            import random
+            rng = random.Random(2024)
+            self.session_neurons = [rng.randint(256, 1024) for _ in range(a.sessions)]
+            self.cfg = default_model_config()
+            self.mods = ["ap", "behavior"]
+            self.extra = None
+            self.n_beh, self.T = 2, 100
+            self.neurons = max(self.session_neurons)
+            self.chan = [sum(self.session_neurons) / len(self.session_neurons), 2]
+            self.desc = (f"configs[3]: multi-session pre-training, {a.sessions} synthetic sessions with "
+                         f"{min(self.session_neurons)}-{max(self.session_neurons)} neurons (seeded), per-session embedders "
+                         "and heads selected by eid, shared mm.yaml default transformer, one session per batch")
+        elif self.scaled:
             self.cfg = scaled_model_config()
             self.mods = ["ap", "beh0", "beh1", "beh2", "beh3"]
             self.extra = {m: 1 for m in self.mods[1:]}
@@ -86,12 +103,23 @@ class Workload:
         self.Ld = self.cfg["decoder"]["transformer"]["n_layers"]
         self.S = self.T * len(self.mods)
 
+    def session_of(self, step):
+        return step % len(self.session_neurons)
+
     def build(self):
-        from multi_modal_foundation_model_b200.model import build_model
+        from multi_modal_foundation_model_b200.model import MultiSessionMultiModal, build_model
+        if self.multi:
+            chans = {f"session-{k:02d}": {"ap": n, "behavior": 2} for k, n in enumerate(self.session_neurons)}
+            return MultiSessionMultiModal(chans, self.mods, self.cfg)
         return build_model(self.neurons, self.n_beh, self.cfg, avail_mod=tuple(self.mods), extra_channels=self.extra)
 
     def batch(self, B, step, pin=False):
         from multi_modal_foundation_model_b200.synthetic import make_batch
+        if self.multi:
+            k = self.session_of(step)
+            out = make_batch(B, self.session_neurons[k], self.n_beh, self.T, step=step, pin=pin)
+            out["eid"] = [f"session-{k:02d}"] * B
+            return out
         return make_batch(B, self.neurons, self.n_beh, self.T, step=step, pin=pin)
 
     def inputs_of(self, batch):
@@ -108,7 +136,11 @@ class Workload:
     def flops_fwd_per_trial(self) -> float:
         """SURVEY.md section 8d 'Algorithmic work per trial' (dense attention, 2 FLOPs per multiply-add)."""
         T, S, H, I = self.T, self.S, self.H, self.I
-        f = sum(2 * (2 * T * C * 2 * C + 2 * T * 2 * C * H) + 2 * T * H * C for C in self.chan)
+        if self.multi:   # mean over the sessions
+            f = sum(2 * (2 * T * C * 2 * C + 2 * T * 2 * C * H) + 2 * T * H * C for C in self.session_neurons) / len(self.session_neurons)
+            f += 2 * (2 * T * 2 * 4 + 2 * T * 4 * H) + 2 * T * H * 2
+        else:
+            f = sum(2 * (2 * T * C * 2 * C + 2 * T * 2 * C * H) + 2 * T * H * C for C in self.chan)
         f += self.Le * (8 * S * H * H + 4 * S * S * H + 4 * S * H * I)
         f += self.Ld * (16 * S * H * H + 8 * S * S * H + 4 * S * H * I)
         return float(f + 2 * S * H * H)
@@ -142,14 +174,25 @@ def cpu_reference_rate(a, seconds: float, min_steps: int = 2, fixed_steps: int =
     cfg = wl.cfg
     torch.manual_seed(42)
     model = wl.build()
-    P = {k: v.detach() for k, v in model.state_dict().items()}
-    for k in list(P):
-        if k.startswith("decoder_embeddings.") and k.endswith("mod_emb.weight"):
-            P[k] = P[k.replace("decoder_embeddings.", "encoder_embeddings.")]
+    SD = {k: v.detach() for k, v in model.state_dict().items()}
+
+    def params_for(step):
+        if wl.multi:   # the batch's session: its embedders under the reference's single-session names
+            pre = model.session_prefix(f"session-{wl.session_of(step):02d}")
+            P = {(k[len(pre):] if k.startswith(pre) else k): v for k, v in SD.items()
+                 if k.startswith(pre) or not k.startswith("session_embeddings.")}
+        else:
+            P = dict(SD)
+        for k in list(P):
+            if k.startswith("decoder_embeddings.") and k.endswith("mod_emb.weight"):
+                P[k] = P[k.replace("decoder_embeddings.", "encoder_embeddings.")]
+        return P
+
     spec = orc.OracleSpec.from_config(cfg, wl.mods)
     B = a.cpu_batch
 
     def one(step):
+        P = params_for(step)
         batch = wl.batch(B, step)
         attn = batch["time_attn_mask"]
         mode = MODES[step % 3]
@@ -291,20 +334,28 @@ def main():
     B = a.batch
 
     # rank r's shard of every global batch: its own seeded trials (weak scaling: B per GPU)
-    host_batches = [wl.batch(B, 1000 * rank + i, pin=True) for i in range(3)]
+    NB = len(wl.session_neurons) if wl.multi else 3    # multi-session: one batch per session, visited round-robin
+    first = (rank * (NB // max(world, 1))) if wl.multi else 1000 * rank
+    host_batches = [wl.batch(B, first + i, pin=True) for i in range(NB)]
     dev_batches = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host_batches]
-    dev_dicts = [make_mod_dict(dev_batches[i], wl.mods, MODES[i], device=dev) for i in range(3)]
+    dev_dicts = [make_mod_dict(dev_batches[i], wl.mods, MODES[i % 3], device=dev) for i in range(NB)]
 
     def step_resident(i):
-        md = {k: dict(v) for k, v in dev_dicts[i % 3].items()}
+        md = {k: dict(v) for k, v in dev_dicts[i % NB].items()}
         out = model(md)
         out.loss.backward()
         model.zero_grad(set_to_none=True)
         return out
 
+    from multi_modal_foundation_model_b200.synthetic import DevicePrefetcher
+    pf = DevicePrefetcher(dev)
+
     def step_e2e(i):
-        hb = host_batches[i % 3]
-        db = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}   # H2D
+        # every step copies one batch host -> device (pinned memory, side stream: batch i+1 moves while step i computes)
+        if pf._next is None:
+            pf.put(host_batches[i % NB])
+        db = pf.get()                                                                                  # H2D of batch i
+        pf.put(host_batches[(i + 1) % NB])                                                             # H2D of batch i+1
         md = make_mod_dict(db, wl.mods, MODES[i % 3], device=dev)
         out = model(md)
         out.loss.backward()
@@ -329,7 +380,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for i in range(max(a.warmup, 3)):
+    for i in range(max(a.warmup, 3, 3 * NB if wl.multi else 0)):   # every session's plan built, run and graph-captured
         step_resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -343,7 +394,7 @@ def main():
     opt = AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, eps=1e-8)
 
     def step_optim(i):
-        md = {k: dict(v) for k, v in dev_dicts[i % 3].items()}
+        md = {k: dict(v) for k, v in dev_dicts[i % NB].items()}
         out = model(md)
         out.loss.backward()
         opt.step()
@@ -359,7 +410,7 @@ def main():
         step_e2e(i)
     ms_e2e = timed(step_e2e, a.steps)
     e2e_value = B * n_gpus * a.steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values() if torch.is_tensor(v))
+    h2d = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches) // NB
 
     pl = eng.last_plan
     launches = (ops.count_kernels(pl.fwd_calls) + ops.count_kernels(pl.bwd_calls)) * a.steps

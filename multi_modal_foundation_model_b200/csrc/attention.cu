@@ -1439,6 +1439,61 @@ MMFM_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+
+// ---- helpers of the fused backward: keep bits -> byte-msb words -> 32-bit pair masks (no per-element bit tests) ----
+MMFM_DEVINL uint32_t prmt_b(uint32_t a, uint32_t sel) {   // prmt, sign-replicating selector mode (nibble bit 3)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+// 8 keep bits (n-tile n = 0..3 of this 32-column chunk, e = 0/1 at bit 2n+e) -> two words whose byte msbs carry them:
+// word 0 <- bits 0..3 (n = 0, 1), word 1 <- bits 4..7 (n = 2, 3).  x * 0x10204080 moves bit k to bit 8k+7 (k < 4)
+// and the partial products never collide, so the msbs are exact.
+MMFM_DEVINL void keep_msb_words(uint32_t bits8, uint32_t (&w)[2]) {
+  w[0] = (bits8 & 0xFu) * 0x10204080u;
+  w[1] = ((bits8 >> 4) & 0xFu) * 0x10204080u;
+}
+// probabilities of one 16-column half of a chunk: p (packed bf16) and p * keep (packed bf16)
+template <bool MASKED, bool DROP, int HF>
+MMFM_DEVINL void bwd_prob_half(const uint32_t (&rs)[16], uint32_t aw, float sl2, float lse2,
+                               const uint32_t (&km)[4][2], uint32_t* pk, uint32_t (&pdk)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float e0 = fast_exp2(fmaf(__uint_as_float(rs[2 * t]), sl2, -lse2));
+    float e1 = fast_exp2(fmaf(__uint_as_float(rs[2 * t + 1]), sl2, -lse2));
+    if (MASKED) {   // select, never multiply: masked columns may hold stale TMEM bits
+      if (!((aw >> (16 * HF + 2 * t)) & 1u)) e0 = 0.f;
+      if (!((aw >> (16 * HF + 2 * t + 1)) & 1u)) e1 = 0.f;
+    }
+    const uint32_t pp = pack_bf16x2(e0, e1);
+    pk[t] = pp;
+    if (DROP) {
+      // pair T = 8*HF + t of the chunk: n-tile n = T/4, quad lane ql = T%4 -> word n/2 of km[ql], byte pair n&1
+      const int T = 8 * HF + t, n = T >> 2;
+      pdk[t] = pp & prmt_b(km[T & 3][n >> 1], (n & 1) ? 0xBBAAu : 0x9988u);
+    } else {
+      pdk[t] = pp;
+    }
+  }
+}
+// dS of one 16-column half: ds = p_drop * dP - p * delta  (= p * (keep * dP - delta)), packed bf16
+template <bool MASKED>
+MMFM_DEVINL void bwd_ds_half(const uint32_t (&rd)[16], uint32_t aw16, float dl, const uint32_t* pk, const uint32_t* pdk,
+                             uint32_t (&dsk)[8]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float p0 = __uint_as_float(pk[t] << 16), p1 = __uint_as_float(pk[t] & 0xFFFF0000u);
+    const float q0 = __uint_as_float(pdk[t] << 16), q1 = __uint_as_float(pdk[t] & 0xFFFF0000u);
+    float s0 = fmaf(q0, __uint_as_float(rd[2 * t]), -p0 * dl);
+    float s1 = fmaf(q1, __uint_as_float(rd[2 * t + 1]), -p1 * dl);
+    if (MASKED) {
+      if (!((aw16 >> (2 * t)) & 1u)) s0 = 0.f;
+      if (!((aw16 >> (2 * t + 1)) & 1u)) s1 = 0.f;
+    }
+    dsk[t] = pack_bf16x2(s0, s1);
+  }
+}
+
 template <bool DROP>
 __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_fused_tc_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -1552,45 +1607,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_fused_tc_kernel(
     tc_fence_after();
 
     // ---------------- pass A: probabilities ----------------
-    uint32_t pk[2][16];   // p as packed bf16, kept for pass B
+    uint32_t pk[2][16];    // p as packed bf16, kept for pass B
+    uint32_t pdq[2][16];   // p * keep as packed bf16, kept for pass B (dS = p_drop * dP - p * delta)
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u >= nmine) break;
       const int c = grp + 4 * u;
       const uint32_t aw = aws[u];
-      uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+      uint32_t km[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
       if (DROP) {
         const uint2 w2 = kpre[u];
-        const int sh = 8 * (c & 1);
-        kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
-        kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
+        const int sh = 8 * (c & 1);   // second 32-column chunk of the 64-key block: n-tiles 4..7 -> bits 8..15
+        keep_msb_words((w2.x & 0xFFFFu) >> sh, km[0]);
+        keep_msb_words((w2.x >> 16) >> sh, km[1]);
+        keep_msb_words((w2.y & 0xFFFFu) >> sh, km[2]);
+        keep_msb_words((w2.y >> 16) >> sh, km[3]);
+      }
+      const bool masked = __any_sync(0xffffffffu, aw != 0xFFFFFFFFu);
+      uint32_t rs[2][16];
+      tmem_ld16(t_row + 32u * c, rs[0]);
+      tmem_ld16(t_row + 32u * c + 16u, rs[1]);
+      tmem_ld_wait();
+      uint32_t pdk[2][8];
+      if (masked) {
+        bwd_prob_half<true, DROP, 0>(rs[0], aw, sl2, lse2, km, &pk[u][0], pdk[0]);
+        bwd_prob_half<true, DROP, 1>(rs[1], aw, sl2, lse2, km, &pk[u][8], pdk[1]);
+      } else {
+        bwd_prob_half<false, DROP, 0>(rs[0], aw, sl2, lse2, km, &pk[u][0], pdk[0]);
+        bwd_prob_half<false, DROP, 1>(rs[1], aw, sl2, lse2, km, &pk[u][8], pdk[1]);
       }
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        uint32_t rs[16];
-        tmem_ld16(t_row + 32u * c + 16u * hf, rs);
-        tmem_ld_wait();
-        uint32_t pdk[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int k0 = 16 * hf + 2 * t, k1 = k0 + 1;
-          float e0 = fast_exp2(fmaf(__uint_as_float(rs[2 * t]), sl2, -lse2));
-          float e1 = fast_exp2(fmaf(__uint_as_float(rs[2 * t + 1]), sl2, -lse2));
-          if (!((aw >> k0) & 1u)) e0 = 0.f;
-          if (!((aw >> k1) & 1u)) e1 = 0.f;
-          pk[u][8 * hf + t] = pack_bf16x2(e0, e1);
-          if (DROP) {
-            if (!((kw[(k0 & 7) >> 1] >> (2 * (k0 >> 3) + (k0 & 1))) & 1u)) e0 = 0.f;
-            if (!((kw[(k1 & 7) >> 1] >> (2 * (k1 >> 3) + (k1 & 1))) & 1u)) e1 = 0.f;
-          }
-          pdk[t] = pack_bf16x2(e0, e1);
-        }
+        for (int t = 0; t < 8; ++t) pdq[u][8 * hf + t] = pdk[hf][t];
         // two 16-byte pieces (8 keys each) of this row into the P_drop slab
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const int j16 = (c & 1) * 4 + hf * 2 + q4;
           const uint32_t addr = sPd + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
-          st_shared_v4(addr, pdk[4 * q4], pdk[4 * q4 + 1], pdk[4 * q4 + 2], pdk[4 * q4 + 3]);
+          st_shared_v4(addr, pdk[hf][4 * q4], pdk[hf][4 * q4 + 1], pdk[hf][4 * q4 + 2], pdk[hf][4 * q4 + 3]);
         }
       }
     }
@@ -1626,37 +1681,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_fused_tc_kernel(
       if (u >= nmine) break;
       const int c = grp + 4 * u;
       const uint32_t aw = aws[u];
-      uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
-      if (DROP) {
-        const uint2 w2 = kpre[u];
-        const int sh = 8 * (c & 1);
-        kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
-        kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
+      const bool masked = __any_sync(0xffffffffu, aw != 0xFFFFFFFFu);
+      uint32_t rd[2][16];
+      tmem_ld16(t_row + 32u * c, rd[0]);
+      tmem_ld16(t_row + 32u * c + 16u, rd[1]);
+      tmem_ld_wait();
+      uint32_t dsk[2][8];
+      if (masked) {
+        bwd_ds_half<true>(rd[0], aw & 0xFFFFu, dl, &pk[u][0], &pdq[u][0], dsk[0]);
+        bwd_ds_half<true>(rd[1], aw >> 16, dl, &pk[u][8], &pdq[u][8], dsk[1]);
+      } else {
+        bwd_ds_half<false>(rd[0], 0xFFFFu, dl, &pk[u][0], &pdq[u][0], dsk[0]);
+        bwd_ds_half<false>(rd[1], 0xFFFFu, dl, &pk[u][8], &pdq[u][8], dsk[1]);
       }
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        uint32_t rd[16];
-        tmem_ld16(t_row + 32u * c + 16u * hf, rd);
-        tmem_ld_wait();
-        uint32_t dsk[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int k0 = 16 * hf + 2 * t, k1 = k0 + 1;
-          const float2 pp = unpack_bf16x2(pk[u][8 * hf + t]);
-          float d0 = __uint_as_float(rd[2 * t]), d1 = __uint_as_float(rd[2 * t + 1]);
-          if (DROP) {
-            if (!((kw[(k0 & 7) >> 1] >> (2 * (k0 >> 3) + (k0 & 1))) & 1u)) d0 = 0.f;
-            if (!((kw[(k1 & 7) >> 1] >> (2 * (k1 >> 3) + (k1 & 1))) & 1u)) d1 = 0.f;
-          }
-          const float s0 = ((aw >> k0) & 1u) ? pp.x * (d0 - dl) : 0.f;
-          const float s1 = ((aw >> k1) & 1u) ? pp.y * (d1 - dl) : 0.f;
-          dsk[t] = pack_bf16x2(s0, s1);
-        }
 #pragma unroll
         for (int q4 = 0; q4 < 2; ++q4) {
           const int j16 = (c & 1) * 4 + hf * 2 + q4;
           const uint32_t addr = sdS + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
-          st_shared_v4(addr, dsk[4 * q4], dsk[4 * q4 + 1], dsk[4 * q4 + 2], dsk[4 * q4 + 3]);
+          st_shared_v4(addr, dsk[hf][4 * q4], dsk[hf][4 * q4 + 1], dsk[hf][4 * q4 + 2], dsk[hf][4 * q4 + 3]);
         }
       }
     }

@@ -104,6 +104,12 @@ MMFM_DEVINL void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint6
       : "memory");
 }
 
+// Pull one box of the tensor into L2 without touching shared memory: issued a tile or two ahead of the real load, it
+// turns the ring's HBM latency into L2 latency, so the same bytes in flight sustain a multiple of the bandwidth.
+MMFM_DEVINL void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@
 //              token-zeroing / residual, direct vectorised global stores
 // Several CTAs are resident per SM (smem- and TMEM-limited), so one CTA's epilogue overlaps another's main loop.
 #include "common.cuh"
+#include <stdlib.h>
 #include "host_util.h"
 #include "../../include/mmfm_b200.h"
 
@@ -93,7 +94,8 @@ enum EpiKind : int {
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
-                                                                 const mmfm_gemm_args p, int tiles_n, int n_tiles) {
+                                                                 const mmfm_gemm_args p, int tiles_n, int n_tiles,
+                                                                 int bstat) {
   constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
   constexpr uint32_t kBBytes = BN * kBK * 2;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -102,9 +104,14 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
   constexpr int kHalf = BN / (kEpiWarps / 4);   // columns per epilogue warp
   constexpr bool GEN = EPI == EPI_GENERIC;
 
+  // Weight-stationary mode (bstat): the grid is a multiple of tiles_n, so every tile of this CTA has the same column
+  // block; its whole K extent of B (<= half of the ring area) is loaded ONCE and stays resident, the ring carries A
+  // k-blocks only.  These skinny-K GEMMs are bound by L2 -> SM traffic, which this halves.
+  constexpr int kMaxStages = 8;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t b_full;
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -115,15 +122,21 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = (p.K + kBK - 1) / kBK;
+  const uint32_t b_res_bytes = bstat ? (uint32_t)nkb * kBBytes : 0u;
+  const uint32_t ring_base = smem_base + b_res_bytes;
+  const uint32_t st_bytes = bstat ? kABytes : kStageBytes;
+  uint32_t nst = bstat ? (STAGES * kStageBytes - b_res_bytes) / kABytes : (uint32_t)STAGES;
+  if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(&b_full, 1);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], kEpiWarps);
@@ -142,15 +155,29 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
   if (warp == 0) {
     if (elect_one()) {
       uint32_t it = 0;
+      if (bstat) {
+        const int n0 = ((int)blockIdx.x % tiles_n) * BN;
+        mbar_arrive_expect_tx(&b_full, b_res_bytes);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d_addr(smem_base + kb * kBBytes, &tmB, &b_full, kb * kBK, n0);
+      }
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+        // L2 prefetch of the activation rows this CTA needs two tiles from now (the ring itself holds about one
+        // tile); the CTA that owns the first column tile of that row block fetches for all its neighbours
+        {
+          const int t2 = tile + 2 * (int)gridDim.x;
+          if (t2 < n_tiles && (t2 % tiles_n == 0 || tiles_n > (int)gridDim.x)) {
+            const int m2 = (t2 / tiles_n) * kBM;
+            for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&tmA, kb * kBK, m2);
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES;
-          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-          const uint32_t a_dst = smem_base + s * kStageBytes;
+          const uint32_t s = it % nst;
+          if (it >= nst) mbar_wait(&empty_bar[s], ((it / nst) - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[s], st_bytes);
+          const uint32_t a_dst = ring_base + s * st_bytes;
           tma_load_2d_addr(a_dst, &tmA, &full_bar[s], kb * kBK, m0);
-          tma_load_2d_addr(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, n0);
+          if (!bstat) tma_load_2d_addr(a_dst + kABytes, &tmB, &full_bar[s], kb * kBK, n0);
         }
       }
     }
@@ -158,17 +185,18 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
       uint32_t it = 0, t = 0;
+      if (bstat) mbar_wait(&b_full, 0);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const uint32_t buf = t & 1u;
         if (t >= 2) mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1);   // epilogue drained this TMEM buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          const uint32_t s = it % nst;
+          mbar_wait(&full_bar[s], (it / nst) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + s * kStageBytes;
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_addr = ring_base + s * st_bytes;
+          const uint32_t b_addr = bstat ? smem_base + kb * kBBytes : a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024, 2);
@@ -251,6 +279,95 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
       __syncwarp();
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
       tc_fence_after();
+      // Interior tiles of the two commonest flavours take a straight-line path: no edge / alignment / remap tests, bf16
+      // staging for bf16 outputs, 16-byte global accesses (these GEMMs are bound by epilogue instruction issue).
+      const bool interior = (m0 + kBM <= p.M) && (n0 + BN <= p.N);
+      if ((EPI == EPI_PLAIN_BF16 || EPI == EPI_RES_F32) && interior && p.remap_T == 0 && kHalf == 32) {
+        const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase;
+        if (EPI == EPI_PLAIN_BF16) {
+          // bf16 staging (half the shared-memory traffic of the fp32 tile; row-strided 16-byte global stores straight
+          // from registers were measured 35 % slower than this staged, row-contiguous form)
+          constexpr int kPitchH = BN + 8;   // bf16 staging pitch (elements): 16 bytes mod 128 -> phase A conflict-free
+          bf16* stage_h = reinterpret_cast<bf16*>(stage_f);
+          bf16* my_row_h = stage_h + row_l * kPitchH + cbase;
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(t_row + (uint32_t)c0, acc);
+            tmem_ld_wait();
+            uint32_t h[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&my_bias[c0 + j4 * 4]);
+              h[2 * j4] = pack_bf16x2(__uint_as_float(acc[4 * j4]) + b4.x, __uint_as_float(acc[4 * j4 + 1]) + b4.y);
+              h[2 * j4 + 1] = pack_bf16x2(__uint_as_float(acc[4 * j4 + 2]) + b4.z, __uint_as_float(acc[4 * j4 + 3]) + b4.w);
+            }
+            *reinterpret_cast<uint4*>(my_row_h + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(my_row_h + c0 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          // phase B: 4 lanes x 16 bytes per row, 8 rows per step; the two rows of a quarter-warp are 4 apart (64 bytes
+          // mod 128 in the staging tile: no bank conflicts)
+          const int lr = (lane >> 3) + 4 * ((lane >> 2) & 1), lc = (lane & 3) * 8;
+          bf16* dst = reinterpret_cast<bf16*>(p.D) + ((long long)m0 + quad * 32 + lr) * p.ldd + n0 + cbase + lc;
+          const bf16* src = stage_h + (quad * 32 + lr) * kPitchH + cbase + lc;
+#pragma unroll
+          for (int st8 = 0; st8 < 4; ++st8)
+            *reinterpret_cast<uint4*>(dst + (long long)st8 * 8 * p.ldd) = *reinterpret_cast<const uint4*>(src + st8 * 8 * kPitchH);
+        } else {
+          float* my_row = stage_f + row_l * kPitch + cbase;
+#pragma unroll
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(t_row + (uint32_t)c0, acc);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&my_bias[c0 + j4 * 4]);
+              v[4 * j4 + 0] = __uint_as_float(acc[4 * j4 + 0]) + b4.x;
+              v[4 * j4 + 1] = __uint_as_float(acc[4 * j4 + 1]) + b4.y;
+              v[4 * j4 + 2] = __uint_as_float(acc[4 * j4 + 2]) + b4.z;
+              v[4 * j4 + 3] = __uint_as_float(acc[4 * j4 + 3]) + b4.w;
+            }
+            if (drop) {
+              const uint4 w = drop_bytes16(seed, p.drop.site, (uint64_t)r, drop_gpr, (uint32_t)((n0 + cbase + c0) >> 4));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (drop_byte(w, j) < p.drop.thresh) ? 0.f : v[j] * p.drop.scale;
+            }
+            if (zero) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<float4*>(my_row + c0 + j4 * 4) =
+                  make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          // phase B: 8 lanes x 16 bytes per row, 4 rows per step; the residual rows of all steps are requested first
+          const int lr = lane >> 3, lc = (lane & 7) * 4;
+          const long long grow = (long long)m0 + quad * 32 + lr;
+          const float* rsrc = p.res + grow * p.ldr + n0 + cbase + lc;
+          float* dst = reinterpret_cast<float*>(p.D) + grow * p.ldd + n0 + cbase + lc;
+          const float* src = stage_f + (quad * 32 + lr) * kPitch + cbase + lc;
+          float4 rv[8];
+#pragma unroll
+          for (int s8 = 0; s8 < 8; ++s8) rv[s8] = __ldg(reinterpret_cast<const float4*>(rsrc + (long long)s8 * 4 * p.ldr));
+#pragma unroll
+          for (int s8 = 0; s8 < 8; ++s8) {
+            const float4 v = *reinterpret_cast<const float4*>(src + s8 * 4 * kPitch);
+            *reinterpret_cast<float4*>(dst + (long long)s8 * 4 * p.ldd) =
+                make_float4(v.x + rv[s8].x, v.y + rv[s8].y, v.z + rv[s8].z, v.w + rv[s8].w);
+          }
+        }
+        __syncwarp();   // staging rows are re-written by this warp's next tile
+        continue;
+      }
       if (warp_has_cols) {
         const uint32_t t_row = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase;
         float* my_row = stage_f + row_l * kPitch + cbase;
@@ -430,8 +547,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
 
   if (warp == 0) {
     if (elect_one()) {
+      constexpr int kAhead = 2 * STAGES;   // L2 prefetch distance in k-blocks (the ring holds STAGES of them)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
+        if (kb + kAhead < nkb) {
+          // every dY box is read by all KI tiles, every X box by all NO tiles: one of them prefetches for the others
+          const int rp = r_begin + (kb + kAhead) * kBK;
+          if (blockIdx.x == 0) { tma_prefetch_l2_2d(&tmY, no0, rp); tma_prefetch_l2_2d(&tmY, no0 + 64, rp); }
+          if (blockIdx.y == 0) { tma_prefetch_l2_2d(&tmX, ki0, rp); tma_prefetch_l2_2d(&tmX, ki0 + 64, rp); }
+        }
         if (kb >= STAGES) mbar_wait(&empty_bar[s], ((kb / STAGES) - 1) & 1);
         mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
         const uint32_t a_dst = smem_base + s * kStageBytes;
@@ -601,10 +725,27 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
                                          (int)smem));
     attr_set = true;
   }
-  const int tiles_n = (a->N + BN - 1) / BN;
-  const int n_tiles = tiles_n * ((a->M + kBM - 1) / kBM);
-  const int grid = n_tiles < device_sm_count() ? n_tiles : device_sm_count();
-  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a, tiles_n, n_tiles);
+  const int tiles_n = (a->N + BN - 1) / BN, tiles_m = (a->M + kBM - 1) / kBM;
+  const int n_tiles = tiles_n * tiles_m;
+  int grid = n_tiles < device_sm_count() ? n_tiles : device_sm_count();
+  // weight-stationary schedule: B's whole K extent fits half of the ring area and the grid can be a multiple of tiles_n
+  // (measured neutral on B200 -- these GEMMs turned out to be bound by epilogue instruction issue, not by L2 -> SM
+  // traffic -- so the streamed-B schedule stays the default; MMFM_GEMM_BSTAT=1 enables it for A/B measurements)
+  static int bstat_env = -1;
+  if (bstat_env < 0) {
+    const char* e = getenv("MMFM_GEMM_BSTAT");
+    bstat_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int nkb = (a->K + kBK - 1) / kBK;
+  int bstat = 0;
+  if (bstat_env && (size_t)nkb * BN * kBK * 2 * 2 <= (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) &&
+      tiles_n <= device_sm_count() && tiles_m > 1) {
+    int per_n = device_sm_count() / tiles_n;
+    if (per_n > tiles_m) per_n = tiles_m;
+    grid = per_n * tiles_n;
+    bstat = 1;
+  }
+  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a, tiles_n, n_tiles, bstat);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -100,3 +100,34 @@ def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[s
             raise Exception("Training objective not implemented yet.")
         mod_dict[mod] = d
     return mod_dict
+
+
+class DevicePrefetcher:
+    """Double-buffered host->device staging of trainer batches (pinned host memory): batch i+1 is copied on a side
+    stream while step i computes, so the H2D transfer leaves the critical path.  ``put`` enqueues the copy of the next
+    batch, ``get`` makes the compute stream wait for it and hands the device batch over."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._next = None
+        self._event = None
+
+    def put(self, host_batch: Dict[str, object]) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self._next = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v)
+                          for k, v in host_batch.items()}
+            self._event = torch.cuda.Event()
+            self._event.record(self.stream)
+
+    def get(self) -> Dict[str, object]:
+        if self._next is None:
+            raise RuntimeError("DevicePrefetcher.get() without a pending put()")
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._event)
+        batch, self._next = self._next, None
+        for v in batch.values():
+            if torch.is_tensor(v):
+                v.record_stream(cur)
+        return batch

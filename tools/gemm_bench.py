@@ -55,3 +55,10 @@ BT = R // 2
 xin = mk(BT, 672); w1 = mk(1336, 672)[0]; hid = mk(BT, 1336)
 bench("embed1 [BT,668]x[1336,668]", lambda i: ops.gemm_tn(xin[i][:, :668], w1[:, :668], hid[i]), 2.0 * BT * 1336 * 668, BT * (668 * 2 + 1336 * 2))
 bench("cuBLAS qkv (torch.matmul)", lambda i: torch.matmul(x[i], w_qkv.t(), out=qkv[i]), 2.0 * R * 768 * 256, R * (256 * 2 + 768 * 2))
+# epilogue-only probes: same output shape as qkv, tiny K (the main loop vanishes)
+x64 = mk(R, 64); w64 = mk(3 * H, 64)[0]
+bench("probe qkv-shape K=64 ->bf16", lambda i: ops.gemm_tn(x64[i], w64, qkv[i], bias=b768), 2.0 * R * 768 * 64, R * (64 * 2 + 768 * 2))
+x128 = mk(R, 128); w128 = mk(3 * H, 128)[0]
+bench("probe qkv-shape K=128 ->bf16", lambda i: ops.gemm_tn(x128[i], w128, qkv[i], bias=b768), 2.0 * R * 768 * 128, R * (128 * 2 + 768 * 2))
+x512 = mk(R, 512); w512 = mk(3 * H, 512)[0]
+bench("probe qkv-shape K=512 ->bf16", lambda i: ops.gemm_tn(x512[i], w512, qkv[i], bias=b768), 2.0 * R * 768 * 512, R * (512 * 2 + 768 * 2))
