@@ -440,19 +440,26 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = {}
+        try:   # per-launch DRAM bytes of the same command under ncu (tools/launch_summary.py), default workload only
+            if a.workload == "default":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        except Exception:
+            pass
         top = next(iter(kernel_table))
         d = agg[top]
         if d["flops"]:
             peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None,
+                        "frac": ach / peak, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
+                        "algorithmic_bytes_per_launch": (d["bytes"] / d["n"]) if d["bytes"] else None,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF"}
         else:
             peak = float(peaks.get("hbm_gbs", 6650.0))
             ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": None,
+                        "frac": ach / peak, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
 
     cpu = None

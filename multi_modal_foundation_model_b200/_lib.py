@@ -14,7 +14,7 @@ from typing import List, Optional
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libmmfm_b200.so")
-SOURCES = ["host_util.cu", "gemm.cu", "norm.cu", "attention.cu", "attention_pipe.cu", "attention_bwd_stream.cu", "glue.cu"]
+SOURCES = ["host_util.cu", "gemm.cu", "norm.cu", "attention.cu", "attention_pipe.cu", "attention_bwd_stream.cu", "attention_bwd_persist.cu", "glue.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 
@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(_CSRC, src), "-o", obj]
+        extra = os.environ.get("MMFM_NVCC_EXTRA", "").split()      # e.g. -DMMFM_DBG_TIMING for tools/micro probes
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(_CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
