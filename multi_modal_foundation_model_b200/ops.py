@@ -84,12 +84,9 @@ def run_recorded(calls) -> None:
             check(rc, c[2])
 
 
-# kernels launched per C call (mmfm_attention_bwd = prep + dq + dkv)
-KERNELS_PER_CALL = {"mmfm_attention_bwd": 3}
-
-
 def count_kernels(calls) -> int:
-    return sum(KERNELS_PER_CALL.get(c[2], 1) for c in calls)
+    """Kernels launched by a recorded schedule (a C call is one kernel unless its meta says otherwise)."""
+    return sum(int(c[3].get("kernels", 1)) for c in calls)
 
 
 def run_recorded_timed(calls):
@@ -232,8 +229,12 @@ def attention_fwd(q, k, v, o, lse, key_valid, **kw) -> None:
 
 def attention_bwd(q, k, v, o, lse, key_valid, **kw) -> None:
     a = _attn_args(q, k, v, o, lse, key_valid, **kw)
+    # kernels behind the call: prep + one fused kernel (d_head 32, S <= 256, no modality-separation mask), else
+    # prep + dq + dkv (mirrors the dispatch in csrc/attention.cu)
+    fused = a.d_head == 32 and a.Sq <= 256 and a.Sk <= 256 and not a.mod_q
     _launch("mmfm_attention_bwd", C.byref(a), keep=(a,),
-            meta={"flops": 8.0 * a.B * a.n_heads * a.Sq * a.Sk * a.d_head})   # algorithmic: 2x forward
+            meta={"flops": 8.0 * a.B * a.n_heads * a.Sq * a.Sk * a.d_head,   # algorithmic: 2x forward
+                  "kernels": 2 if fused else 3})
 
 
 def mask_prep(masks: Sequence[Optional[torch.Tensor]], attns: Sequence[torch.Tensor], channels: Sequence[int],
