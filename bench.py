@@ -350,8 +350,14 @@ def main():
     from multi_modal_foundation_model_b200.synthetic import DevicePrefetcher
     pf = DevicePrefetcher(dev)
 
+    host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_losses = []
+
     def step_e2e(i):
         # every step copies one batch host -> device (pinned memory, side stream: batch i+1 moves while step i computes)
+        # and reads its loss back (asynchronous D2H into pinned memory, consumed one step later -- the way a trainer
+        # logs without stalling the launch queue; the last one is consumed right after the timed loop's barrier)
         if pf._next is None:
             pf.put(host_batches[i % NB])
         db = pf.get()                                                                                  # H2D of batch i
@@ -360,7 +366,12 @@ def main():
         out = model(md)
         out.loss.backward()
         model.zero_grad(set_to_none=True)
-        return float(out.loss.item())                                                                  # D2H
+        slot = i & 1
+        host_loss[slot].copy_(out.loss.detach().reshape(1), non_blocking=True)                         # D2H of step i
+        loss_ev[slot].record()
+        if i > 0:
+            loss_ev[slot ^ 1].synchronize()
+            e2e_losses.append(float(host_loss[slot ^ 1][0]))                                            # loss of step i-1
 
     def barrier():
         if world > 1:
@@ -409,6 +420,20 @@ def main():
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e_u8 = None
+    if not wl.scaled:
+        # the same leg with the spike counts shipped as bytes (uint8 wire format, expanded by mmfm_u8_expand on the device)
+        fp32_batches = host_batches
+        host_batches = [dict(hb, spikes_data=hb["spikes_data"].to(torch.uint8).pin_memory()) for hb in fp32_batches]
+        pf._next = None
+        for i in range(3 if not wl.multi else NB):
+            step_e2e(i)
+        ms_e2e_u8 = timed(step_e2e, a.steps)
+        h2d_u8 = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches) // NB
+        host_batches = fp32_batches
+        pf._next = None
+    e2e_losses.append(float(host_loss[(a.steps - 1) & 1][0]))
+    assert all(v == v for v in e2e_losses[-a.steps:]), "non-finite loss in the end-to-end leg"
     e2e_value = B * n_gpus * a.steps / (ms_e2e / 1e3)
     h2d = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches) // NB
 
@@ -448,19 +473,25 @@ def main():
             pass
         top = next(iter(kernel_table))
         d = agg[top]
-        if d["flops"]:
-            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
-                        "algorithmic_bytes_per_launch": (d["bytes"] / d["n"]) if d["bytes"] else None,
-                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF"}
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_bw = float(peaks.get("hbm_gbs", 6650.0))
+        src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        sec = d["ms"] * 1e-3
+        ach_tf = d["flops"] / sec / 1e12 if d["flops"] else 0.0
+        ach_bw = d["bytes"] / sec / 1e9 if d["bytes"] else 0.0
+        # the binding roofline of the family: the larger of (algorithmic flops / tensor peak) and (algorithmic bytes /
+        # HBM peak); the skinny-K GEMMs of the default model (K 256-768, fp32 residual in/out) are HBM-bound
+        if ach_bw / peak_bw >= ach_tf / peak_tf:
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach_bw, "peak": peak_bw, "unit": "GB/s",
+                        "frac": ach_bw / peak_bw, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
+                        "algorithmic_bytes_per_launch": d["bytes"] / d["n"], "tensor_tflops": ach_tf,
+                        "tensor_frac": ach_tf / peak_tf, "peak_source": f"{src} hbm_gbs (copy: read + write)"}
         else:
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                        "frac": ach / peak, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": ach_tf / peak_tf, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
+                        "algorithmic_bytes_per_launch": (d["bytes"] / d["n"]) if d["bytes"] else None,
+                        "hbm_gbs": ach_bw, "hbm_frac": ach_bw / peak_bw,
+                        "peak_source": f"{src} bf16_tflops_sustained"}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
@@ -480,6 +511,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches,
+            "e2e_uint8_wire": (None if ms_e2e_u8 is None else
+                               {"value": B * n_gpus * a.steps / (ms_e2e_u8 / 1e3), "unit": UNIT,
+                                "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 4,
+                                "what": "e2e with spike counts shipped as uint8 and expanded on the device (8f rank 2)"}),
             "with_optimizer": {"value": value_opt, "unit": UNIT, "ms_per_step": ms_opt / a.steps,
                                "what": "fwd + bwd + fused AdamW step (mmfm_adamw_step over the flat fp32 buffers)"},
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,

@@ -201,6 +201,13 @@ int mmfm_cast_bf16_multi(const mmfm_cast_item* items_dev, int n_items, int total
  * scalar loss, trainer/base.py:195 always passes 1) */
 int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stream);
 
+/* ---- batch wire format (spike counts are small non-negative integers, stored as ubyte by
+ *      the reference's datasets, dataset_utils.py:29; the dense fp32 (B,T,N) batch of loader/base.py:436-450 can be
+ *      shipped as bytes) ------------------------------------------------------------------------------------------ */
+/* x: R rows of C bytes (dense).  y32 (optional) fp32 [R, ld32]; y16 (optional) bf16 [R, ld16].  Exact conversions. */
+int mmfm_u8_expand(const unsigned char* x, long long R, int C, float* y32, long long ld32, void* y16, long long ld16,
+                   void* stream);
+
 /* ---- optimizer step (torch.optim.AdamW of train_multi_modal.py:197-202 over the flat
  *      master-parameter / gradient buffers; runs right after backward, trainer/base.py:196-198) ------------------- */
 /* p, g, exp_avg, exp_avg_sq: n fp32 elements each (16-byte aligned).  step >= 1 is the 1-based update count used for

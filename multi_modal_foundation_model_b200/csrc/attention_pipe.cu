@@ -23,6 +23,16 @@
 #include "attn_common.cuh"
 #include <stdlib.h>
 
+#ifdef MMFM_DBG_TIMING
+__device__ long long g_dbg_p[8][64];
+#define DBG_P(slot) do { if (blockIdx.x == 5 && it == 3 && lane == 0 && (warp & 3) == 1) g_dbg_p[warp >> 2][slot] = clock64(); } while (0)
+extern "C" int mmfm_debug_read_pipe(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_dbg_p, sizeof(long long) * (n < 512 ? n : 512));
+}
+#else
+#define DBG_P(slot) do { } while (0)
+#endif
+
 namespace mmfm {
 
 constexpr int kPipeThreads = 576;   // 16 softmax warps + MMA issuer + TMA producer
@@ -312,7 +322,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
 
       // key-validity bits of this batch entry: packed by the producer warp next to the Q stage
       const uint32_t* colbits = s_colbits[it & 1];
+      DBG_P(0);
       mbar_wait(&q_full[it & 1], (uint32_t)((it >> 1) & 1));
+      DBG_P(1);
 
       auto allowed_word = [&](int cg) -> uint32_t {   // cg = global 32-column chunk index
         uint32_t aw = cg < ncw ? colbits[cg] : 0u;
@@ -334,6 +346,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
         const int cg0 = (j * bn) >> 5;
         mbar_wait(&s_full[X], cnt & 1u);
         tc_fence_after();
+        DBG_P(2);
         // ---------------- pass 1: block maximum over this group's columns, then across the two groups ----------------
         float bm = -INFINITY;
         if (active) {
@@ -353,8 +366,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
             }
           }
         }
+        DBG_P(3);
         s_red[X][cnt & 1u][g][row] = bm;
         named_bar_sync(1 + X, 256);
+        DBG_P(4);
         bm = fmaxf(s_red[X][cnt & 1u][0][row], s_red[X][cnt & 1u][1][row]);
         if (active) {
           const float m_new = fmaxf(m_run, bm);
@@ -384,13 +399,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
             uint32_t mw[4][4];   // keep words (msb of each byte) of this block: [quad lane ql][word]
             if (DROP) {
               const uint32_t kbg = (uint32_t)((j * bn) >> 6) + (uint32_t)kb;
+              uint4 w4[4];
+              pdrop_bytes_x4(seed_p, p.drop_p.site, prow, (uint32_t)nkb_tot, kbg, w4);
 #pragma unroll
               for (int ql = 0; ql < 4; ++ql) {
-                const uint4 w = pdrop_bytes(seed_p, p.drop_p.site, prow, (uint32_t)nkb_tot, kbg, (uint32_t)ql);
-                mw[ql][0] = keep_msb(w.x, c4, le128);
-                mw[ql][1] = keep_msb(w.y, c4, le128);
-                mw[ql][2] = keep_msb(w.z, c4, le128);
-                mw[ql][3] = keep_msb(w.w, c4, le128);
+                mw[ql][0] = keep_msb(w4[ql].x, c4, le128);
+                mw[ql][1] = keep_msb(w4[ql].y, c4, le128);
+                mw[ql][2] = keep_msb(w4[ql].z, c4, le128);
+                mw[ql][3] = keep_msb(w4[ql].w, c4, le128);
               }
               if (i < p.Sq)
                 *reinterpret_cast<uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb_tot + kbg) * 4) =
@@ -421,6 +437,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
           }
           tmem_st_wait();
         }
+        DBG_P(5);
         tc_fence_before();
         mbar_arrive(&p_ready[X]);
         ++cnt;
@@ -429,9 +446,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
       // ---------------- epilogue: O / l, output dropout, bf16 rows + LSE (each group stores half of the row) ----------
       s_sum[X][it & 1][g][row] = l;
       named_bar_sync(1 + X, 256);
+      DBG_P(6);
       l = s_sum[X][it & 1][0][row] + s_sum[X][it & 1][1][row];
       mbar_wait(&pv_done[X], (cnt - 1u) & 1u);
       tc_fence_after();
+      DBG_P(7);
       if (active) {
         float inv = l > 0.f ? 1.0f / l : 0.f;
         if (DROP) inv *= p.drop_p.scale;
@@ -462,6 +481,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
           }
         }
       }
+      DBG_P(8);
       tc_fence_before();   // O was read out: the next item's first P.V may overwrite it once p_ready fires
     }
   }

@@ -110,6 +110,14 @@ MMFM_DEVINL void bwd_ds_half(const uint32_t (&rd)[16], uint32_t aw16, float dl, 
 }
 
 
+// the four quad-lane calls of one 64-key block at once (g = (row*nblk + blk)*4 + ql: the low two counter bits are ql and
+// g is a multiple of 4, so the +ql never carries into the high word)
+MMFM_DEVINL void pdrop_bytes_x4(unsigned long long seed, uint32_t site, unsigned long long row, uint32_t nblk,
+                                uint32_t blk, uint4 (&w)[4]) {
+  const unsigned long long g = (row * nblk + blk) * 4ull;
+  philox4x32_x4((uint32_t)g, (uint32_t)(g >> 32), site, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+}
+
 // attention_pipe.cu: persistent warp-specialised tcgen05 forward (any Sk; no modality-separation mask)
 int launch_attn_fwd_pipe(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
 // attention_bwd_stream.cu: tcgen05 backward pair for long sequences (runs after the prep kernel)

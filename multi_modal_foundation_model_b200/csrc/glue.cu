@@ -545,6 +545,34 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     upd(p[i], g[i], m[i], v[i]);
 }
 
+// uint8 spike counts -> fp32 and / or bf16 (the loader's counts are small non-negative
+// integers stored as sparse ubyte, dataset_utils.py:29; shipping them as bytes cuts the H2D copy 4x and both
+// conversions are exact).  One thread converts 16 consecutive bytes of a row (rows are C bytes, C % 16 need not hold).
+__global__ void __launch_bounds__(256) u8_expand_kernel(const unsigned char* __restrict__ x, long long total, int C,
+                                                         float* __restrict__ y32, long long ld32, bf16* __restrict__ y16,
+                                                         long long ld16) {
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; e < total;
+       e += (long long)gridDim.x * blockDim.x * 16) {
+    const long long r = e / C;
+    int c = (int)(e - r * C);
+    const int n = (int)min((long long)16, total - e);
+    unsigned char v[16];
+    if (n == 16 && ((reinterpret_cast<uintptr_t>(x) + e) & 15) == 0) {
+      *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(x + e));
+    } else {
+      for (int k = 0; k < n; ++k) v[k] = x[e + k];
+    }
+    long long rr = r;
+    for (int k = 0; k < n; ++k) {
+      if (c == C) { c = 0; ++rr; }
+      const float f = (float)v[k];
+      if (y32) y32[rr * ld32 + c] = f;
+      if (y16) y16[rr * ld16 + c] = __float2bfloat16_rn(f);
+      ++c;
+    }
+  }
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -719,6 +747,16 @@ extern "C" int mmfm_adamw_step(float* p, const float* g, float* exp_avg, float* 
   adamw_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                          weight_decay, (float)(1.0 / bc1),
                                                                          (float)(1.0 / sqrt(bc2)));
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_u8_expand(const unsigned char* x, long long R, int C, float* y32, long long ld32, void* y16,
+                              long long ld16, void* stream) {
+  MMFM_REQUIRE(x && (y32 || y16) && R > 0 && C > 0, "mmfm_u8_expand: bad arguments");
+  MMFM_REQUIRE((!y32 || ld32 >= C) && (!y16 || ld16 >= C), "mmfm_u8_expand: row pitch smaller than the row");
+  const long long total = R * (long long)C;
+  u8_expand_kernel<<<ew_grid(total / 16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, total, C, y32, ld32, (bf16*)y16, ld16);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -267,8 +267,10 @@ class Arena:
 class Plan:
     """All buffers + the recorded forward / backward launch lists for one (batch size, train/eval) shape."""
 
-    def __init__(self, eng: "Engine", B: int, training: bool, session=None, arena: Optional[Arena] = None):
+    def __init__(self, eng: "Engine", B: int, training: bool, session=None, arena: Optional[Arena] = None,
+                 u8_mods: Tuple[str, ...] = ()):
         self.eng, self.B, self.training = eng, B, training
+        self.u8_mods = tuple(u8_mods)      # modalities whose inputs / targets arrive as uint8 counts (wire format)
         self.arena_bytes = 0
         if arena is not None:
             arena.reset()
@@ -306,6 +308,10 @@ class Plan:
         # ---- static inputs -------------------------------------------------------------------------------
         self.inp = {m.name: f32(B, T, m.C) for m in mods}
         self.tgt = {m.name: f32(B, T, m.C) for m in mods}
+        # byte staging of the uint8 wire format: expanded on the device (inputs -> bf16 GEMM operand, targets -> fp32)
+        self.inp_u8 = {n: torch.zeros(B, T, eng_c, device=dev, dtype=torch.uint8)
+                       for n, eng_c in ((m.name, m.C) for m in mods) if n in self.u8_mods}
+        self.tgt_u8 = {n: torch.zeros_like(t) for n, t in self.inp_u8.items()}
         self.attn = {m.name: i64(B, T) for m in mods}
         self.ts = {m.name: i64(B, T) for m in mods}
         self.mask = {m.name: i64(B, T) for m in mods}
@@ -441,7 +447,12 @@ class Plan:
                 else:
                     if m.name not in self.inb:
                         self.inb[m.name] = b16(BT, m.C)
-                        ops.cast_bf16(self.inp[m.name].view(BT, m.C), self.inb[m.name])
+                        if m.name in self.u8_mods:
+                            ops.u8_expand(self.inp_u8[m.name].view(BT, m.C), None, self.inb[m.name], R=BT, Cc=m.C)
+                            ops.u8_expand(self.tgt_u8[m.name].view(BT, m.C), self.tgt[m.name].view(BT, m.C), None,
+                                          R=BT, Cc=m.C)
+                        else:
+                            ops.cast_bf16(self.inp[m.name].view(BT, m.C), self.inb[m.name])
                     A[pre + ".hid"] = b16(BT, 2 * m.C)
                     ops.gemm_tn(self.inb[m.name], sh.nat[pre + ".token_embed"], A[pre + ".hid"], bias=b1,
                                 act=eng.embed_act, act_scale=eng.embed_scale)
@@ -750,7 +761,7 @@ class Engine:
         self.T: Optional[int] = None
         self.store = ParamStore(model, self.device)
         self.shadows = Shadows(self.store, model, self.sessions)
-        self.plans: Dict[Tuple[int, bool, Any], Plan] = {}
+        self.plans: Dict[Tuple[int, bool, Any, Tuple[str, ...]], Plan] = {}
         self.arenas: Dict[Tuple[int, bool], Arena] = {}
         self.ddp = None          # set by parallel.DataParallel
         import os as _os
@@ -759,14 +770,14 @@ class Engine:
         self._grad_views = None
 
     # ---------------------------------------------------------------------------------------------------
-    def _plan(self, B: int, T: int, training: bool, session=None) -> Plan:
+    def _plan(self, B: int, T: int, training: bool, session=None, u8_mods: Tuple[str, ...] = ()) -> Plan:
         if self.T is None:
             self.T = T
         elif self.T != T:
             self.plans.clear()
             self.arenas.clear()
             self.T = T
-        key = (B, training, session)
+        key = (B, training, session, u8_mods)
         pl = self.plans.get(key)
         if pl is None:
             arena = None
@@ -779,7 +790,7 @@ class Engine:
                     nbytes = probe.arena_bytes + (1 << 20)
                     del probe
                     arena = self.arenas[(B, training)] = Arena(nbytes, self.device)
-            pl = Plan(self, B, training, session, arena)
+            pl = Plan(self, B, training, session, arena, u8_mods)
             self.plans[key] = pl
         return pl
 
@@ -804,7 +815,12 @@ class Engine:
             raise MmfmError("first modality must be (B,T,C)")
         B, T = d0["inputs"].shape[:2]
         training = bool(model.training)
-        pl = self._plan(B, T, training, session)
+        # uint8 wire format (spike counts as bytes): only for modalities that take the GEMM embedder path
+        u8_mods = tuple(m.name for m in mods if not m.small and mod_dict[m.name]["inputs"].dtype == torch.uint8)
+        for m in mods:
+            if mod_dict[m.name]["inputs"].dtype == torch.uint8 and m.name not in u8_mods:
+                raise MmfmError(f"modality {m.name}: uint8 inputs are only supported for spike-count modalities (C > {SMALL_C})")
+        pl = self._plan(B, T, training, session, u8_mods)
         for m in mods:
             d = mod_dict[m.name]
             if d["inputs"].dim() == 2:                                   # mm.py:248-250
@@ -815,8 +831,14 @@ class Engine:
                                           "(UnboundLocalError at mm.py:272); only masking_mode=None is supported")
             if tuple(d["inputs"].shape) != (B, T, m.C):
                 raise MmfmError(f"modality {m.name}: inputs shape {tuple(d['inputs'].shape)} != {(B, T, m.C)}")
-            pl.inp[m.name].copy_(d["inputs"], non_blocking=True)
-            pl.tgt[m.name].copy_(d["targets"], non_blocking=True)
+            if m.name in u8_mods:
+                if d["targets"].dtype != torch.uint8:
+                    raise MmfmError(f"modality {m.name}: uint8 inputs need uint8 targets")
+                pl.inp_u8[m.name].copy_(d["inputs"], non_blocking=True)
+                pl.tgt_u8[m.name].copy_(d["targets"], non_blocking=True)
+            else:
+                pl.inp[m.name].copy_(d["inputs"], non_blocking=True)
+                pl.tgt[m.name].copy_(d["targets"], non_blocking=True)
             pl.attn[m.name].copy_(d["inputs_attn_mask"], non_blocking=True)
             pl.ts[m.name].copy_(d["inputs_timestamp"], non_blocking=True)
             im = d.get("inputs_modality")

@@ -135,7 +135,11 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, M: Optional[in
     a.drop = drop.c()
     a.remap_T, a.remap_S, a.remap_off = remap
     a.row_zero = _p(row_zero)
-    _launch("mmfm_gemm_tn", C.byref(a), keep=(a,), meta={"flops": 2.0 * a.M * a.N * a.K, "tag": f"gemm_tn {a.M}x{a.N}x{a.K}"})
+    mn = float(a.M) * a.N
+    nbytes = 2.0 * a.M * a.K + 2.0 * a.N * a.K + mn * (4 if a.d_fp32 else 2)      # algorithmic: A + B + D ...
+    nbytes += (2.0 * mn if D2 is not None else 0.0) + (4.0 * mn if res is not None else 0.0) + (2.0 * mn if aux is not None else 0.0)
+    _launch("mmfm_gemm_tn", C.byref(a), keep=(a,),
+            meta={"flops": 2.0 * a.M * a.N * a.K, "bytes": nbytes, "tag": f"gemm_tn {a.M}x{a.N}x{a.K}"})
 
 
 def gemm_wgrad(dY: torch.Tensor, X: torch.Tensor, dW: torch.Tensor, *, R: Optional[int] = None,
@@ -148,7 +152,7 @@ def gemm_wgrad(dY: torch.Tensor, X: torch.Tensor, dW: torch.Tensor, *, R: Option
     KI = KI if KI is not None else X.shape[1]
     _launch("mmfm_gemm_wgrad", dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), R, NO, KI, dW.data_ptr(),
             ldw if ldw is not None else KI, _p(dbias),
-            meta={"flops": 2.0 * R * NO * KI, "tag": f"wgrad {R}x{NO}x{KI}"})
+            meta={"flops": 2.0 * R * NO * KI, "bytes": 2.0 * R * (NO + KI) + 4.0 * NO * KI, "tag": f"wgrad {R}x{NO}x{KI}"})
 
 
 def colsum_bf16(dY: torch.Tensor, out: torch.Tensor, *, R: Optional[int] = None, NO: Optional[int] = None) -> None:
@@ -171,6 +175,13 @@ def cast_bf16_multi(items_dev: torch.Tensor, n_items: int, total_tiles: int) -> 
 
 def scale_inplace(x: torch.Tensor, scale_dev: torch.Tensor) -> None:
     _launch("mmfm_scale_inplace", x.data_ptr(), x.numel(), scale_dev.data_ptr())
+
+
+def u8_expand(x: torch.Tensor, y32: Optional[torch.Tensor], y16: Optional[torch.Tensor], *, R: int, Cc: int) -> None:
+    """uint8 [R, Cc] (dense) -> fp32 [R, *] and / or bf16 [R, *] (row pitches from the tensors)."""
+    assert x.dtype == torch.uint8 and x.is_contiguous()
+    _launch("mmfm_u8_expand", x.data_ptr(), R, Cc, _p(y32), y32.stride(0) if y32 is not None else 0, _p(y16),
+            y16.stride(0) if y16 is not None else 0, meta={"bytes": float(R) * Cc * (1 + (4 if y32 is not None else 0) + (2 if y16 is not None else 0))})
 
 
 def adamw_step(p: torch.Tensor, g: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,

@@ -249,3 +249,32 @@ def test_multi_session_matches_oracle_per_session():
     arena = next(iter(eng.arenas.values())).buf
     lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel()
     assert all(lo <= pl.xs[0].data_ptr() < hi for pl in eng.plans.values())   # residual streams alias one arena
+
+
+def test_uint8_wire_format_is_exact():
+    """spike counts shipped as bytes and expanded on the device give bit-identical results to the fp32
+    batch (both conversions are exact)."""
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    torch.manual_seed(4)
+    model = build_model(72, 2, small_config()).cuda().eval()
+    batch = make_batch(3, 72, 2, 100, step=9)
+    g = torch.Generator().manual_seed(1)
+    masks = {m: (torch.rand(3, 100, generator=g) < 0.3).long() for m in ("ap", "behavior")}
+    res = []
+    for as_u8 in (False, True):
+        md = _mod_dict(batch["spikes_data"], batch["target"], batch["time_attn_mask"], batch["spikes_timestamps"], masks)
+        if as_u8:
+            md["ap"]["inputs"] = md["ap"]["inputs"].to(torch.uint8)
+            md["ap"]["targets"] = md["ap"]["targets"].to(torch.uint8)
+        out = model(md)
+        out.loss.backward()
+        torch.cuda.synchronize()
+        res.append((out.loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()},
+                    out.mod_preds["ap"].clone()))
+        model.zero_grad(set_to_none=True)
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][2], res[1][2])
+    for n in res[0][1]:
+        # split-R weight gradients accumulate with floating-point atomics: equal up to summation order
+        assert torch.allclose(res[0][1][n], res[1][1][n], rtol=1e-4, atol=1e-7), n
