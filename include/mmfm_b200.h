@@ -47,7 +47,10 @@ enum mmfm_act {
   MMFM_ACT_GELU = 1,      /* D <- gelu_erf(v); D2 (optional) <- v   (mm_utils.py:51) */
   MMFM_ACT_SOFTSIGN = 2,  /* D <- softsign(v) * act_scale           (encoder_embeddings.py:52) */
   MMFM_ACT_DGELU = 3,     /* D <- v * gelu'(aux)                    (backward of mm_utils.py:51) */
-  MMFM_ACT_DSOFTSIGN = 4  /* D <- v * act_scale * (1-|aux/act_scale|)^2   (backward of encoder_embeddings.py:52) */
+  MMFM_ACT_DSOFTSIGN = 4, /* D <- v * act_scale * (1-|aux/act_scale|)^2   (backward of encoder_embeddings.py:52) */
+  MMFM_ACT_GELU_DG = 5,   /* D <- gelu_erf(v); D2 <- gelu_erf'(v): the derivative is saved instead of the pre-activation
+                             (erf and the Gaussian term are shared), so the backward epilogue is one multiply */
+  MMFM_ACT_MULAUX = 6     /* D <- v * aux                           (backward of MMFM_ACT_GELU_DG) */
 };
 
 typedef struct mmfm_gemm_args {

@@ -131,7 +131,7 @@ class CastItem(C.Structure):
     ]
 
 
-ACT_NONE, ACT_GELU, ACT_SOFTSIGN, ACT_DGELU, ACT_DSOFTSIGN = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_SOFTSIGN, ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU_DG, ACT_MULAUX = 0, 1, 2, 3, 4, 5, 6
 MASK_KEY, MASK_KEY_OR_DIAG, MASK_CAUSAL = 0, 1, 2
 LOSS_POISSON, LOSS_MSE = 0, 1
 

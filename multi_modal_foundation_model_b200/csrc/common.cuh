@@ -104,6 +104,30 @@ MMFM_DEVINL void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint6
       : "memory");
 }
 
+// Multicast load: the box lands at the same shared-memory offset of every CTA of the cluster whose rank bit is set in
+// `mask`, and completes `bytes` on the mbarrier at the same offset in each of them.
+MMFM_DEVINL void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+MMFM_DEVINL void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+MMFM_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+MMFM_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Pull one box of the tensor into L2 without touching shared memory: issued a tile or two ahead of the real load, it
 // turns the ring's HBM latency into L2 latency, so the same bytes in flight sustain a multiple of the bandwidth.
 MMFM_DEVINL void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
@@ -305,6 +329,12 @@ MMFM_DEVINL float gelu_erf_grad(float x) {
   float e;
   const float cdf = 0.5f * (1.0f + erf_poly(x * 0.70710678118654752f, e));
   return fmaf(x * 0.3989422804014327f, e, cdf);   // Phi(x) + x * phi(x), phi(x) = exp(-x^2/2) / sqrt(2 pi)
+}
+MMFM_DEVINL void gelu_erf_both(float x, float& g, float& dg) {   // gelu and its derivative from one erf / exp pair
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_poly(x * 0.70710678118654752f, e));
+  g = x * cdf;
+  dg = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 MMFM_DEVINL float softsign(float x) { return x / (1.0f + fabsf(x)); }
 

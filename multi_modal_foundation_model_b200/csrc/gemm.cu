@@ -84,7 +84,9 @@ enum EpiKind : int {
   EPI_SOFTSIGN = 4,     // D(bf16) = softsign(v) * s
   EPI_DGELU = 5,        // D(bf16) = v * gelu'(aux)
   EPI_DSOFTSIGN = 6,    // D(bf16) = v * s * (1 - |aux/s|)^2
-  EPI_GENERIC = 7
+  EPI_GENERIC = 7,
+  EPI_GELU_DG = 8,      // D2(bf16) = gelu'(v) ; D(bf16) = gelu(v)
+  EPI_MULAUX = 9        // D(bf16) = v * aux
 };
 
 // Persistent: one CTA per SM walks the tile list (n fastest, so concurrently running CTAs share A rows in L2).  The
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
     const int row_l = quad * 32 + lane;            // tile row of this thread (phase A)
     constexpr bool kMayDrop = GEN || EPI == EPI_RES_F32;
     constexpr bool kHasRes = GEN || EPI == EPI_RES_F32;
-    constexpr bool kHasAux = GEN || EPI == EPI_DGELU || EPI == EPI_DSOFTSIGN;
+    constexpr bool kHasAux = GEN || EPI == EPI_DGELU || EPI == EPI_DSOFTSIGN || EPI == EPI_MULAUX;
     bool drop = false;
     unsigned long long seed = 0ull;
     if (kMayDrop) {
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
     const bool f32out = GEN ? (p.d_fp32 != 0) : (EPI == EPI_PLAIN_F32 || EPI == EPI_RES_F32);
     const float inv_scale = 1.0f / p.act_scale;
     const bool has_res = GEN ? (p.res != nullptr) : (EPI == EPI_RES_F32);
-    const bool has_aux = GEN ? (act == MMFM_ACT_DGELU || act == MMFM_ACT_DSOFTSIGN) : kHasAux;
+    const bool has_aux = GEN ? (act == MMFM_ACT_DGELU || act == MMFM_ACT_DSOFTSIGN || act == MMFM_ACT_MULAUX) : kHasAux;
     float* my_bias = s_bias[ew];
     static_assert(kHalf <= 64, "bias slice: at most two values per lane");
     // bias slice of this warp's columns, fetched one tile ahead so its latency is never exposed
@@ -452,6 +454,14 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
               if (EPI == EPI_GELU || (GEN && act == MMFM_ACT_GELU)) {
                 if (!GEN || p.D2) st4_bf16(reinterpret_cast<bf16*>(p.D2) + orow[u] * p.ldd + n, vec_d2, nvalid, v);
                 v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+              } else if (EPI == EPI_GELU_DG || (GEN && act == MMFM_ACT_GELU_DG)) {
+                float4 dg;
+                gelu_erf_both(v.x, v.x, dg.x); gelu_erf_both(v.y, v.y, dg.y);
+                gelu_erf_both(v.z, v.z, dg.z); gelu_erf_both(v.w, v.w, dg.w);
+                if (!GEN || p.D2) st4_bf16(reinterpret_cast<bf16*>(p.D2) + orow[u] * p.ldd + n, vec_d2, nvalid, dg);
+              } else if (EPI == EPI_MULAUX || (GEN && act == MMFM_ACT_MULAUX)) {
+                const float4 a = av[u];
+                v.x *= a.x; v.y *= a.y; v.z *= a.z; v.w *= a.w;
               } else if (EPI == EPI_SOFTSIGN || (GEN && act == MMFM_ACT_SOFTSIGN)) {
                 v.x = softsign(v.x) * p.act_scale; v.y = softsign(v.y) * p.act_scale;
                 v.z = softsign(v.z) * p.act_scale; v.w = softsign(v.w) * p.act_scale;
@@ -490,7 +500,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
                                                                    const __grid_constant__ CUtensorMap tmX, int R,
                                                                    int NO, int KI, float* __restrict__ dW,
                                                                    long long ldw, int rows_per_split,
-                                                                   float* __restrict__ dbias) {
+                                                                   float* __restrict__ dbias, int cx, int cy) {
+  // (cx, cy) = thread-block cluster shape over (KI tiles, NO tiles), 1 or 2 each.  The CTAs of a cluster work on the
+  // same rows: the two KI tiles of a cluster row share their dY boxes, the two NO tiles of a cluster column share their
+  // X boxes, so each CTA loads HALF of what it consumes and TMA-multicasts it to its peer (this kernel is bound by
+  // L2 -> SM traffic: every dY box is needed by all KI tiles and every X box by all NO tiles).
   constexpr int BN = 128;
   constexpr uint32_t kBoxBytes = 64 * kBK * 2;  // [64 rows(k) x 64 cols(mn)] bf16 = 8 KB
   constexpr uint32_t kABytes = 2 * kBoxBytes;
@@ -519,6 +533,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   const int r_end = min(R, r_begin + rows_per_split);
   const int nkb = (r_end - r_begin + kBK - 1) / kBK;  // >= 1 by construction of the grid
   const bool do_bias = (dbias != nullptr) && (blockIdx.x == 0);
+  // cluster geometry: rank = x_local + cx * y_local; peers along x share dY, peers along y share X
+  const bool clustered = cx * cy > 1;
+  const uint32_t rank = clustered ? cluster_ctarank() : 0u;
+  const int xl = (int)rank % cx, yl = (int)rank / cx;
+  const uint16_t mask_x = (uint16_t)(cx == 2 ? (3u << (cx * yl)) : (1u << rank));                 // (0,yl) and (1,yl)
+  const uint16_t mask_y = (uint16_t)(cy == 2 ? ((1u << xl) | (1u << (xl + cx))) : (1u << rank));    // (xl,0) and (xl,1)
+  const uint16_t mask_free = (uint16_t)(mask_x | mask_y);      // CTAs whose loads land in this CTA's stages
+  const uint32_t n_free = (uint32_t)(1 + (cx == 2) + (cy == 2));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
@@ -526,7 +548,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], n_free);   // this CTA and the peers it multicasts to have drained the stage
     }
     mbar_init(&accum_bar, 1);
     fence_mbar_init();
@@ -542,6 +564,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();   // every CTA's barriers are initialised before a peer's multicast can touch them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -561,10 +584,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
         const uint32_t a_dst = smem_base + s * kStageBytes;
         const int r0 = r_begin + kb * kBK;
         // rows_per_split is a multiple of kBK, so only the global tail (>= R) is zero-filled by TMA
-        tma_load_2d_addr(a_dst, &tmY, &full_bar[s], no0, r0);
-        tma_load_2d_addr(a_dst + kBoxBytes, &tmY, &full_bar[s], no0 + 64, r0);
-        tma_load_2d_addr(a_dst + kABytes, &tmX, &full_bar[s], ki0, r0);
-        tma_load_2d_addr(a_dst + kABytes + kBoxBytes, &tmX, &full_bar[s], ki0 + 64, r0);
+        if (cx == 2) {   // this CTA fetches dY box xl for both KI tiles of its cluster row
+          tma_load_2d_mc(a_dst + xl * kBoxBytes, &tmY, &full_bar[s], no0 + 64 * xl, r0, mask_x);
+        } else {
+          tma_load_2d_addr(a_dst, &tmY, &full_bar[s], no0, r0);
+          tma_load_2d_addr(a_dst + kBoxBytes, &tmY, &full_bar[s], no0 + 64, r0);
+        }
+        if (cy == 2) {   // ... and X box yl for both NO tiles of its cluster column
+          tma_load_2d_mc(a_dst + kABytes + yl * kBoxBytes, &tmX, &full_bar[s], ki0 + 64 * yl, r0, mask_y);
+        } else {
+          tma_load_2d_addr(a_dst + kABytes, &tmX, &full_bar[s], ki0, r0);
+          tma_load_2d_addr(a_dst + kABytes + kBoxBytes, &tmX, &full_bar[s], ki0 + 64, r0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -589,7 +620,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
             umma_bf16(tmem_base + BN, da, d1, idesc_b, (kb > 0 || k > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&empty_bar[s]);
+        if (clustered) umma_commit_mc(&empty_bar[s], mask_free);   // frees the stage here and tells the peers that feed it
+        else umma_commit(&empty_bar[s]);
       }
       umma_commit(&accum_bar);
     }
@@ -645,6 +677,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();   // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -772,6 +805,10 @@ static int pick_epi(const mmfm_gemm_args* a) {
   switch (a->act) {
     case MMFM_ACT_NONE: return a->D2 ? EPI_GENERIC : (f32 ? EPI_PLAIN_F32 : EPI_PLAIN_BF16);
     case MMFM_ACT_GELU: return (!f32 && a->D2 && al(a->D2, 8)) ? EPI_GELU : EPI_GENERIC;
+    case MMFM_ACT_GELU_DG: return (!f32 && a->D2 && al(a->D2, 8)) ? EPI_GELU_DG : EPI_GENERIC;
+    case MMFM_ACT_MULAUX:
+      if (f32 || a->D2 || a->ldaux % 4 != 0 || !al(a->aux, 8)) return EPI_GENERIC;
+      return EPI_MULAUX;
     case MMFM_ACT_SOFTSIGN: return (!f32 && !a->D2) ? EPI_SOFTSIGN : EPI_GENERIC;
     case MMFM_ACT_DGELU:
     case MMFM_ACT_DSOFTSIGN:
@@ -785,8 +822,10 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   MMFM_REQUIRE(a != nullptr, "mmfm_gemm_tn: null args");
   MMFM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mmfm_gemm_tn: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   MMFM_REQUIRE(a->A && a->B && a->D, "mmfm_gemm_tn: null operand");
-  MMFM_REQUIRE(a->act >= MMFM_ACT_NONE && a->act <= MMFM_ACT_DSOFTSIGN, "mmfm_gemm_tn: bad act %d", a->act);
-  MMFM_REQUIRE(!(a->act >= MMFM_ACT_DGELU) || a->aux, "mmfm_gemm_tn: act %d needs aux", a->act);
+  MMFM_REQUIRE(a->act >= MMFM_ACT_NONE && a->act <= MMFM_ACT_MULAUX, "mmfm_gemm_tn: bad act %d", a->act);
+  MMFM_REQUIRE(!(a->act == MMFM_ACT_DGELU || a->act == MMFM_ACT_DSOFTSIGN || a->act == MMFM_ACT_MULAUX) || a->aux,
+               "mmfm_gemm_tn: act %d needs aux", a->act);
+  MMFM_REQUIRE(a->act != MMFM_ACT_GELU_DG || a->D2, "mmfm_gemm_tn: MMFM_ACT_GELU_DG needs the D2 buffer");
   MMFM_REQUIRE(a->drop.thresh == 0 || a->drop.seed, "mmfm_gemm_tn: dropout without seed pointer");
   MMFM_REQUIRE(a->drop.thresh < 256, "mmfm_gemm_tn: dropout threshold out of range");
   MMFM_REQUIRE(!(a->row_zero && a->remap_T == 0) || a->remap_S > 0, "mmfm_gemm_tn: row_zero needs remap_S");
@@ -801,6 +840,8 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
     case EPI_SOFTSIGN: return launch_tn_bn<EPI_SOFTSIGN>(a, st);
     case EPI_DGELU: return launch_tn_bn<EPI_DGELU>(a, st);
     case EPI_DSOFTSIGN: return launch_tn_bn<EPI_DSOFTSIGN>(a, st);
+    case EPI_GELU_DG: return launch_tn_bn<EPI_GELU_DG>(a, st);
+    case EPI_MULAUX: return launch_tn_bn<EPI_MULAUX>(a, st);
     default: return launch_tn_bn<EPI_GENERIC>(a, st);
   }
 }
@@ -824,15 +865,40 @@ extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, lo
   }
   const int tiles = ((NO + kBM - 1) / kBM) * ((KI + 127) / 128);
   const int kblocks = (R + kBK - 1) / kBK;
-  int splits = (2 * device_sm_count() + tiles - 1) / tiles;
+  static int waves_x2 = -1;   // MMFM_WGRAD_CTAS_X2: target CTA count in half-SM-counts (default 4 = two CTAs per SM)
+  if (waves_x2 < 0) {
+    const char* e = getenv("MMFM_WGRAD_CTAS_X2");
+    waves_x2 = e ? atoi(e) : 4;
+    if (waves_x2 < 1) waves_x2 = 4;
+  }
+  // all CTAs must be resident at once (two per SM): a split count rounded UP spills a few CTAs into a second wave that
+  // costs as much as the first (measured 43 us vs 34 us on the QKV shape), so round down
+  int splits = (waves_x2 * device_sm_count() / 2) / tiles;
   if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   int rows_per_split = ((kblocks + splits - 1) / splits) * kBK;
   splits = (R + rows_per_split - 1) / rows_per_split;
   dim3 grid((KI + 127) / 128, (NO + kBM - 1) / kBM, splits);
-  gemm_wgrad_kernel<STAGES><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(tmY, tmX, R, NO, KI, dW, ldw,
-                                                                                 rows_per_split, dbias);
-  MMFM_CHECK_CUDA(cudaGetLastError());
+  static int mc_env = -1;   // MMFM_WGRAD_MULTICAST=1: 2x2 clusters, each CTA loads half of its boxes and multicasts them
+  if (mc_env < 0) {
+    const char* e = getenv("MMFM_WGRAD_MULTICAST");
+    mc_env = (e && e[0] == '1') ? 1 : 0;   // measured slower than independent CTAs (lock-step stages): off by default
+  }
+  const int cx = (mc_env && grid.x % 2 == 0) ? 2 : 1, cy = (mc_env && grid.y % 2 == 0) ? 2 : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cx;
+  attr[0].val.clusterDim.y = cy;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMFM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<STAGES>, tmY, tmX, R, NO, KI, dW, ldw, rows_per_split, dbias,
+                                     cx, cy));
   return 0;
 }
 

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_NONE, ACT_SOFTSIGN, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
+from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_SOFTSIGN, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
                    MASK_KEY, MASK_KEY_OR_DIAG, CastItem, MmfmError, lib)
 from .ops import NO_DROP, DropSpec
 
@@ -475,9 +475,11 @@ class Plan:
         def mlp_block(pre, x_in, x_out, ln_name, p_drop, layer, side, inter):
             A[ln_name] = b16(R, H)
             self._ln_fwd(x_in, ln_name, A[ln_name], self.stats)
-            A[pre + ".u"], A[pre + ".g"] = b16(R, inter), b16(R, inter)
+            # saved for backward: gelu(u) (operand of the down projection and of its wgrad) and gelu'(u) -- the derivative
+            # instead of the pre-activation, so the backward epilogue is a single multiply
+            A[pre + ".dg"], A[pre + ".g"] = b16(R, inter), b16(R, inter)
             ops.gemm_tn(A[ln_name], sh.nat[pre + ".up_proj"], A[pre + ".g"], bias=self._bias([pre + ".up_proj.bias"]),
-                        act=ACT_GELU, D2=A[pre + ".u"])
+                        act=ACT_GELU_DG if eng.save_gelu_grad else ACT_GELU, D2=A[pre + ".dg"])
             ops.gemm_tn(A[pre + ".g"], sh.nat[pre + ".down_proj"], x_out, bias=self._bias([pre + ".down_proj.bias"]),
                         drop=self._drop(SITE_MLP, layer, side, p_drop), res=x_in)
 
@@ -570,7 +572,8 @@ class Plan:
 
         def mlp_bwd(pre, x_in, ln_name, Gs, inter, dxb, drop_prev):
             duv = du[:, :inter]
-            lin_bwd(Gb, A[pre + ".g"], pre + ".down_proj", pre + ".down_proj", duv, act=ACT_DGELU, aux=A[pre + ".u"])
+            lin_bwd(Gb, A[pre + ".g"], pre + ".down_proj", pre + ".down_proj", duv,
+                    act=ACT_MULAUX if eng.save_gelu_grad else ACT_DGELU, aux=A[pre + ".dg"])
             lin_bwd(duv, A[ln_name], pre + ".up_proj", pre + ".up_proj", dh)
             self._ln_bwd(dh, x_in, ln_name, Gs, Gs, dxb, drop_prev)
 
@@ -766,6 +769,8 @@ class Engine:
         self.ddp = None          # set by parallel.DataParallel
         import os as _os
         self.use_graphs = _os.environ.get("MMFM_CUDA_GRAPHS", "1") != "0"
+        # MLP forward saves gelu'(u) (default) or the pre-activation u (MMFM_GELU_SAVE=u: A/B of the two backward epilogues)
+        self.save_gelu_grad = _os.environ.get("MMFM_GELU_SAVE", "dg") != "u"
         self.last_plan: Optional[Plan] = None
         self._grad_views = None
 

@@ -40,7 +40,8 @@ def test_gemm_tn_bias(M, N, K, out_fp32):
 
 def test_gemm_tn_epilogues():
     from multi_modal_foundation_model_b200 import ops
-    from multi_modal_foundation_model_b200._lib import ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_SOFTSIGN
+    from multi_modal_foundation_model_b200._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX,
+                                                        ACT_SOFTSIGN)
     M, N, K = 400, 512, 256
     A, B = _mk(M, K, seed=3, scale=0.5), _mk(N, K, seed=4, scale=0.1)
     bias = torch.randn(N, device="cuda") * 0.1
@@ -51,6 +52,16 @@ def test_gemm_tn_epilogues():
     ops.gemm_tn(A, B, D, bias=bias, act=ACT_GELU, D2=D2)
     _close(D, torch.nn.functional.gelu(v), 8e-3, "gelu")
     _close(D2, v, 8e-3, "gelu pre-activation")
+    # GELU + saved derivative (what the engine records), and its backward epilogue D = v * aux
+    ops.gemm_tn(A, B, D, bias=bias, act=ACT_GELU_DG, D2=D2)
+    vg = v.clone().requires_grad_(True)
+    torch.nn.functional.gelu(vg).sum().backward()
+    _close(D, torch.nn.functional.gelu(v), 8e-3, "gelu (dg flavour)")
+    _close(D2, vg.grad, 8e-3, "gelu derivative")
+    auxm = _mk(M, N, seed=8)
+    Dm = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, Dm, act=ACT_MULAUX, aux=auxm)
+    _close(Dm, (A.float() @ B.float().T) * auxm.float(), 8e-3, "mulaux")
     # softsign * scale
     ops.gemm_tn(A, B, D, bias=bias, act=ACT_SOFTSIGN, act_scale=1.5)
     _close(D, torch.nn.functional.softsign(v) * 1.5, 8e-3, "softsign")

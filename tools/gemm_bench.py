@@ -4,7 +4,7 @@ import sys
 import torch
 sys.path.insert(0, '.')
 from multi_modal_foundation_model_b200 import ops
-from multi_modal_foundation_model_b200._lib import ACT_GELU, ACT_DGELU
+from multi_modal_foundation_model_b200._lib import ACT_GELU, ACT_DGELU, ACT_GELU_DG, ACT_MULAUX
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 51200
 NCOPY = 6
@@ -43,6 +43,8 @@ w_d = mk(H, I)[0]
 bench("down  [R,512]x[256,512] drop+res", lambda i: ops.gemm_tn(g[i], w_d, out[i], bias=b256, res=res[i], drop=ops.DropSpec(seed, 3, 0.4)), 2.0 * R * 256 * 512, R * (512 * 2 + 256 * 4 * 2))
 w_dT = mk(I, H)[0]
 bench("ddown [R,256]x[512,256] dgelu", lambda i: ops.gemm_tn(x[i], w_dT, g[i], act=ACT_DGELU, aux=u[i]), 2.0 * R * 512 * 256, R * (256 * 2 + 512 * 2 * 2))
+bench("up    ... gelu + saved derivative", lambda i: ops.gemm_tn(x[i], w_u, g[i], bias=b512, act=ACT_GELU_DG, D2=u[i]), 2.0 * R * 512 * 256, R * (256 * 2 + 512 * 2 * 2))
+bench("ddown ... multiply by saved deriv", lambda i: ops.gemm_tn(x[i], w_dT, g[i], act=ACT_MULAUX, aux=u[i]), 2.0 * R * 512 * 256, R * (256 * 2 + 512 * 2 * 2))
 w_uT = mk(H, I)[0]
 bench("dup   [R,512]x[256,512] ->bf16", lambda i: ops.gemm_tn(g[i], w_uT, x[i]), 2.0 * R * 256 * 512, R * (512 * 2 + 256 * 2))
 w_qT = mk(H, 3 * H)[0]
