@@ -86,17 +86,23 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __rest
   }
 }
 
-// grid (T, B-chunks); block H/4 threads (one float4 column group each).  Consecutive samples that hit the same
-// position row are summed in registers before one red.global per column.
+// grid (T, B-chunks); block = (H/4 float4 column groups) x kAsmLanes sample lanes: lane l walks samples b0+l, b0+l+L, ..
+// so several independent row loads are in flight per column group.  Consecutive samples of a lane that hit the same
+// position row are summed in registers before one red.global per column; the modality-embedding sums of the lanes are
+// combined in shared memory (one atomic per column per CTA).
+constexpr int kAsmLanes = 4;
 __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const float* __restrict__ g2,
                                           const long long* __restrict__ ts, float* __restrict__ dpos,
                                           float* __restrict__ dmod, int B, int T, int S, int off, int H, int bchunk) {
+  extern __shared__ float4 sm_acc[];                      // [kAsmLanes][H/4]
   const int t = blockIdx.x;
   const int b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
-  for (int c = threadIdx.x; c < (H >> 2); c += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = acc;
-    long long cur = -1;
-    for (int b = b0; b < b1; ++b) {
+  const int ncol = H >> 2;
+  const int c = threadIdx.x % ncol, sl = threadIdx.x / ncol;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = acc;
+  long long cur = -1;
+  if (sl < kAsmLanes) {
+    for (int b = b0 + sl; b < b1; b += kAsmLanes) {
       const long long row = ((long long)b * S + off + t) * H;
       float4 v = __ldg(reinterpret_cast<const float4*>(g + row) + c);
       if (g2) {
@@ -121,8 +127,18 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const flo
       float* d = dpos + cur * H + c * 4;
       atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
     }
+    sm_acc[sl * ncol + c] = accm;
+  }
+  __syncthreads();
+  if (sl == 0) {
+    float4 tot = sm_acc[c];
+#pragma unroll
+    for (int l = 1; l < kAsmLanes; ++l) {
+      const float4 o = sm_acc[l * ncol + c];
+      tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
+    }
     float* dm = dmod + c * 4;
-    atomicAdd(dm, accm.x); atomicAdd(dm + 1, accm.y); atomicAdd(dm + 2, accm.z); atomicAdd(dm + 3, accm.w);
+    atomicAdd(dm, tot.x); atomicAdd(dm + 1, tot.y); atomicAdd(dm + 2, tot.z); atomicAdd(dm + 3, tot.w);
   }
 }
 
@@ -276,6 +292,175 @@ __global__ void smallc_embed_bwd_kernel(const float* __restrict__ in, const floa
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c)
       if (c < C) atomicAdd(dW1 + h * C + c, aw1[c]);
+  }
+}
+
+// ---- fast path of the small-channel embedder for C <= 2 (the model's behaviour streams): a thread owns 16 consecutive
+// hidden columns of a row, i.e. exactly one Philox group, so the dropout stream costs one Philox call per 16 outputs
+// (the row-per-CTA kernels above run one call per output element and are bound by it).  gridDim * blockDim is a multiple
+// of the groups per row, so a thread's column group -- and with it its slice of W2 -- is fixed for the whole loop.
+template <int C>
+__global__ void __launch_bounds__(256) smallc_embed_fwd16_kernel(
+    const float* __restrict__ in, const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ W2,
+    const float* __restrict__ b2, const float* __restrict__ emb, float* __restrict__ x, float* __restrict__ hid,
+    const unsigned char* __restrict__ row_zero, DropCfg drop, float act_scale, int act, int B, int T, int S, int off, int H) {
+  constexpr int C2 = 2 * C;
+  const int gpr = H >> 4;                                   // 16-column groups per row
+  const long long slots = (long long)B * T * gpr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long slot0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(slot0 % gpr);
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  float w1[C2][C], bb1[C2], w2[16][C2], bb2[16];
+#pragma unroll
+  for (int j = 0; j < C2; ++j) {
+    bb1[j] = b1 ? b1[j] : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) w1[j][c] = W1[j * C + c];
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    bb2[k] = b2 ? b2[16 * g + k] : 0.f;
+#pragma unroll
+    for (int j = 0; j < C2; ++j) w2[k][j] = W2[(16 * g + k) * C2 + j];
+  }
+  for (long long slot = slot0; slot < slots; slot += stride) {
+    const long long r = slot / gpr;
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    float hj[C2];
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+      float a = bb1[j];
+#pragma unroll
+      for (int c = 0; c < C; ++c) a = fmaf(__ldg(in + r * C + c), w1[j][c], a);
+      hj[j] = act_fwd(a, act, act_scale);
+      if (g == 0) hid[r * C2 + j] = hj[j];
+    }
+    const bool zero = row_zero && row_zero[off + t];
+    uint4 w = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (drop.thresh != 0u) w = drop_bytes16(seed, drop.site, (uint64_t)r, (uint32_t)gpr, (uint32_t)g);
+    const long long orow = (b * S + off + t) * H + 16 * g;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const float4 e = __ldg(reinterpret_cast<const float4*>(emb + orow + k4));
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a = bb2[k4 + u];
+#pragma unroll
+        for (int j = 0; j < C2; ++j) a = fmaf(hj[j], w2[k4 + u][j], a);
+        if (drop.thresh != 0u) a = drop_byte(w, k4 + u) < drop.thresh ? 0.f : a * drop.scale;
+        v[u] = zero ? 0.f : a;
+      }
+      *reinterpret_cast<float4*>(x + orow + k4) = make_float4(v[0] + e.x, v[1] + e.y, v[2] + e.z, v[3] + e.w);
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) smallc_embed_bwd16_kernel(
+    const float* __restrict__ in, const float* __restrict__ hid, const float* __restrict__ W2, const float* __restrict__ dx,
+    const unsigned char* __restrict__ row_zero, DropCfg drop, float act_scale, int act, float* __restrict__ dW1,
+    float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2, int B, int T, int S, int off, int H) {
+  constexpr int C2 = 2 * C;
+  __shared__ float red[4096 + 256];                         // [CTA row slot][H + 1]: (256/gpr) * (16 gpr + 1) floats
+  const int gpr = H >> 4;                                   // 16-column groups per row: a power of two <= 32
+  const long long slots = (long long)B * T * gpr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const long long slot0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)(slot0 % gpr);
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  float w2[16][C2], ab2[16], aw2[16][C2], aw1[C2][C], ab1[C2];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    ab2[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < C2; ++j) { w2[k][j] = W2[(16 * g + k) * C2 + j]; aw2[k][j] = 0.f; }
+  }
+#pragma unroll
+  for (int j = 0; j < C2; ++j) {
+    ab1[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) aw1[j][c] = 0.f;
+  }
+  // the loop bound is warp-uniform (the shuffles below need all 32 lanes); a row past the end contributes zeros
+  for (long long wb = slot0 - lane; wb < slots; wb += stride) {
+    const long long slot = wb + lane;
+    const bool valid = slot < slots;
+    const long long r = valid ? slot / gpr : 0;
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    float d[16];
+    const bool zero = !valid || (row_zero && row_zero[off + t]);
+    const long long orow = (b * S + off + t) * H + 16 * g;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const float4 v = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(dx + orow + k4));
+      d[k4] = v.x; d[k4 + 1] = v.y; d[k4 + 2] = v.z; d[k4 + 3] = v.w;
+    }
+    if (drop.thresh != 0u && !zero) {
+      const uint4 w = drop_bytes16(seed, drop.site, (uint64_t)r, (uint32_t)gpr, (uint32_t)g);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) d[k] = drop_byte(w, k) < drop.thresh ? 0.f : d[k] * drop.scale;
+    }
+    float hj[C2], dh[C2];
+#pragma unroll
+    for (int j = 0; j < C2; ++j) { hj[j] = __ldg(hid + r * C2 + j); dh[j] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      ab2[k] += d[k];
+#pragma unroll
+      for (int j = 0; j < C2; ++j) {
+        aw2[k][j] = fmaf(d[k], hj[j], aw2[k][j]);
+        dh[j] = fmaf(d[k], w2[k][j], dh[j]);
+      }
+    }
+    // sum dh over the gpr lanes of the row
+#pragma unroll
+    for (int j = 0; j < C2; ++j)
+      for (int o = gpr >> 1; o > 0; o >>= 1) dh[j] += __shfl_xor_sync(0xffffffffu, dh[j], o);
+    if (g == 0 && valid) {
+#pragma unroll
+      for (int j = 0; j < C2; ++j) {
+        float v = dh[j];
+        if (act == MMFM_ACT_SOFTSIGN) {   // derivative of act(v)*scale through the saved output a = hid
+          const float tt = 1.0f - fabsf(hj[j] / act_scale);
+          v *= act_scale * tt * tt;
+        } else {
+          v *= act_scale;
+        }
+        ab1[j] += v;
+#pragma unroll
+        for (int c = 0; c < C; ++c) aw1[j][c] = fmaf(v, __ldg(in + r * C + c), aw1[j][c]);
+      }
+    }
+  }
+  // ---- flush: (1 + C2) CTA-wide column reductions over the threads that share a column group, one atomic per column ----
+  const int trow = threadIdx.x / gpr, nrow = 256 / gpr, pitch = H + 1;
+#pragma unroll
+  for (int q = 0; q <= C2; ++q) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[trow * pitch + 16 * g + k] = (q == 0) ? ab2[k] : aw2[k][q == 0 ? 0 : q - 1];
+    __syncthreads();
+    for (int col = threadIdx.x; col < H; col += 256) {
+      float sum = 0.f;
+      for (int rr = 0; rr < nrow; ++rr) sum += red[rr * pitch + col];
+      if (q == 0) atomicAdd(db2 + col, sum);
+      else atomicAdd(dW2 + col * C2 + (q - 1), sum);
+    }
+    __syncthreads();
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int j = 0; j < C2; ++j) {
+      atomicAdd(db1 + j, ab1[j]);
+#pragma unroll
+      for (int c = 0; c < C; ++c) atomicAdd(dW1 + j * C + c, aw1[j][c]);
+    }
   }
 }
 
@@ -624,11 +809,10 @@ extern "C" int mmfm_embed_assemble_bwd(const float* g, const float* g2, const lo
   if (chunks < 1) chunks = 1;
   const int bchunk = (B + chunks - 1) / chunks;
   chunks = (B + bchunk - 1) / bchunk;
-  int threads = H / 4;
-  if (threads > 256) threads = 256;
-  threads = (threads + 31) / 32 * 32;
-  embed_assemble_bwd_kernel<<<dim3(T, chunks), threads, 0, (cudaStream_t)stream>>>(g, g2, ts, dpos, dmod, B, T, S, off,
-                                                                                   H, bchunk);
+  MMFM_REQUIRE(H % 4 == 0 && H / 4 * kAsmLanes <= 1024, "mmfm_embed_assemble_bwd: H=%d not supported (H %% 4, H <= 1024)", H);
+  const int threads = H / 4 * kAsmLanes;
+  embed_assemble_bwd_kernel<<<dim3(T, chunks), threads, (size_t)threads * sizeof(float4), (cudaStream_t)stream>>>(
+      g, g2, ts, dpos, dmod, B, T, S, off, H, bchunk);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -651,6 +835,17 @@ extern "C" int mmfm_smallc_embed_fwd(const float* in, const float* W1, const flo
   MMFM_REQUIRE(C >= 1 && C <= kMaxC, "mmfm_smallc_embed_fwd: C=%d outside [1,%d]", C, kMaxC);
   MMFM_REQUIRE(act == MMFM_ACT_NONE || act == MMFM_ACT_SOFTSIGN, "mmfm_smallc_embed_fwd: bad act %d", act);
   MMFM_REQUIRE(B > 0 && T > 0 && H > 0 && off >= 0 && off + T <= S, "mmfm_smallc_embed_fwd: bad shape");
+  const int gpr = H / 16;
+  if (C <= 2 && H % 16 == 0 && gpr <= 256 && 256 % gpr == 0 && (((uintptr_t)emb | (uintptr_t)x) & 15) == 0) {
+    // thread = one 16-column group: grid sized to a whole number of resident waves, a multiple of the groups per row
+    const long long slots = (long long)B * T * gpr;
+    int grid = 4 * device_sm_count();
+    if ((long long)grid * 256 > slots) grid = (int)((slots + 255) / 256);
+    if (C == 1) smallc_embed_fwd16_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(in, W1, b1, W2, b2, emb, x, hid, row_zero, to_drop(drop), act_scale, act, B, T, S, off, H);
+    else smallc_embed_fwd16_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(in, W1, b1, W2, b2, emb, x, hid, row_zero, to_drop(drop), act_scale, act, B, T, S, off, H);
+    MMFM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   smallc_embed_fwd_kernel<<<B * T, 256, 0, (cudaStream_t)stream>>>(in, W1, b1, W2, b2, emb, x, hid, row_zero,
                                                                    to_drop(drop), act_scale, act, B, T, S, off, C, H);
   MMFM_CHECK_CUDA(cudaGetLastError());
@@ -665,6 +860,16 @@ extern "C" int mmfm_smallc_embed_bwd(const float* in, const float* hid, const fl
   MMFM_REQUIRE(C >= 1 && C <= kMaxC, "mmfm_smallc_embed_bwd: C=%d outside [1,%d]", C, kMaxC);
   MMFM_REQUIRE(H % 32 == 0 && H <= 1024, "mmfm_smallc_embed_bwd: H=%d must be a multiple of 32 and <= 1024", H);
   MMFM_REQUIRE(B > 0 && T > 0 && off >= 0 && off + T <= S, "mmfm_smallc_embed_bwd: bad shape");
+  const int gpr = H / 16;
+  if (C <= 2 && H % 16 == 0 && gpr <= 32 && 32 % gpr == 0 && ((uintptr_t)dx & 15) == 0) {
+    const long long slots = (long long)B * T * gpr;
+    int grid = device_sm_count();        // ~230 registers per thread: one CTA per SM, one wave
+    if ((long long)grid * 256 > slots) grid = (int)((slots + 255) / 256);
+    if (C == 1) smallc_embed_bwd16_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(in, hid, W2, dx, row_zero, to_drop(drop), act_scale, act, dW1, db1, dW2, db2, B, T, S, off, H);
+    else smallc_embed_bwd16_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(in, hid, W2, dx, row_zero, to_drop(drop), act_scale, act, dW1, db1, dW2, db2, B, T, S, off, H);
+    MMFM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const long long R = (long long)B * T;
   int ctas = 2 * device_sm_count();
   int rows_per_cta = (int)((R + ctas - 1) / ctas);
