@@ -35,6 +35,54 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
   const float invH = 1.0f / (float)H;
+  if constexpr (NV > 0 && NV <= 4) {
+    // register path, two rows per warp in flight: both rows' loads are issued before either reduction starts
+    for (long long r0 = ((long long)blockIdx.x * kLnWarps + warp) * 2; r0 < R; r0 += (long long)gridDim.x * kLnWarps * 2) {
+      const bool two = r0 + 1 < R;
+      float4 v[2][NV];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+          v[u][j] = (u == 0 || two) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + u) * H) + lane + 32 * j)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      float mu[2], rs[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+        mu[u] = warp_sum(s) * invH;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const float a = v[u][j].x - mu[u], b = v[u][j].y - mu[u], c = v[u][j].z - mu[u], d = v[u][j].w - mu[u];
+          q += (a * a + b * b) + (c * c + d * d);
+        }
+        rs[u] = rsqrtf(warp_sum(q) * invH + eps);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const long long r = r0 + u;
+        if (lane == 0) {
+          mean[r] = mu[u];
+          rstd[r] = rs[u];
+        }
+        bf16* yr = y + ln_out_row(r, modmajor_T, S, BT) * H;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+          uint2 o;
+          o.x = pack_bf16x2((v[u][j].x - mu[u]) * rs[u] * g.x + b.x, (v[u][j].y - mu[u]) * rs[u] * g.y + b.y);
+          o.y = pack_bf16x2((v[u][j].z - mu[u]) * rs[u] * g.z + b.z, (v[u][j].w - mu[u]) * rs[u] * g.w + b.w);
+          reinterpret_cast<uint2*>(yr)[lane + 32 * j] = o;
+        }
+      }
+    }
+    return;
+  }
   for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
     const float* xr = x + r * H;
     bf16* yr = y + ln_out_row(r, modmajor_T, S, BT) * H;
@@ -199,8 +247,13 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
 using namespace mmfm;
 
 static int ln_grid(int R) {
-  // one row per warp, no cap: the block scheduler balances better than a grid-stride loop with a ragged tail
+  // no cap: the block scheduler balances better than a grid-stride loop with a ragged tail
   return (R + kLnWarps - 1) / kLnWarps;
+}
+static int ln_grid_fwd(int R, int H) {
+  // H <= 512: two rows per warp (see the kernel), so half the CTAs
+  if (H == 128 || H == 256 || H == 512) return (R + 2 * kLnWarps - 1) / (2 * kLnWarps);
+  return ln_grid(R);
 }
 
 // CTAs that are resident at once (whole waves only: the backward ends with per-CTA atomics, so fat CTAs)
@@ -218,7 +271,7 @@ extern "C" int mmfm_layernorm_fwd(const float* x, const float* gamma, const floa
   MMFM_REQUIRE(modmajor_T <= 0 || (S > 0 && S % modmajor_T == 0 && R % S == 0),
                "mmfm_layernorm_fwd: modality-major remap needs S %% T == 0 and R %% S == 0");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ln_grid(R);
+  const int grid = ln_grid_fwd(R, H);
 #define LN_FWD(NV) \
   layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, (bf16*)y, mean, rstd, R, H, eps, modmajor_T, S)
   switch (H) {
