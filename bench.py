@@ -420,6 +420,7 @@ def main():
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, a.steps)
+    pl = eng.last_plan            # the fp32-batch plan: the per-kernel table and the launch count below describe it
     ms_e2e_u8 = None
     if not wl.scaled:
         # the same leg with the spike counts shipped as bytes (uint8 wire format, expanded by mmfm_u8_expand on the device)
@@ -437,7 +438,6 @@ def main():
     e2e_value = B * n_gpus * a.steps / (ms_e2e / 1e3)
     h2d = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches) // NB
 
-    pl = eng.last_plan
     launches = (ops.count_kernels(pl.fwd_calls) + ops.count_kernels(pl.bwd_calls)) * a.steps
 
     # ---- per-kernel timing (events around every launch, separate pass) -> roofline of the dominant kernel ----

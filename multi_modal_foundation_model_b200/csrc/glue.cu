@@ -732,28 +732,27 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 
 // uint8 spike counts -> fp32 and / or bf16 (the loader's counts are small non-negative
 // integers stored as sparse ubyte, dataset_utils.py:29; shipping them as bytes cuts the H2D copy 4x and both
-// conversions are exact).  One thread converts 16 consecutive bytes of a row (rows are C bytes, C % 16 need not hold).
-__global__ void __launch_bounds__(256) u8_expand_kernel(const unsigned char* __restrict__ x, long long total, int C,
+// conversions are exact).
+// VEC: C, both row pitches and all base pointers are multiples of 4 elements -> one thread converts 4 consecutive bytes
+// of a row (uchar4 in, float4 / 2 x bf16x2 out); otherwise one byte per thread.
+template <bool VEC>
+__global__ void __launch_bounds__(256) u8_expand_kernel(const unsigned char* __restrict__ x, long long R, int C,
                                                          float* __restrict__ y32, long long ld32, bf16* __restrict__ y16,
                                                          long long ld16) {
-  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; e < total;
-       e += (long long)gridDim.x * blockDim.x * 16) {
-    const long long r = e / C;
-    int c = (int)(e - r * C);
-    const int n = (int)min((long long)16, total - e);
-    unsigned char v[16];
-    if (n == 16 && ((reinterpret_cast<uintptr_t>(x) + e) & 15) == 0) {
-      *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(x + e));
+  const int per_row = VEC ? (C >> 2) : C;
+  const long long total = R * per_row;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / per_row;
+    const int c = (int)(e - r * per_row) * (VEC ? 4 : 1);
+    if (VEC) {
+      const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(x + r * C + c));
+      const float4 f = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+      if (y32) *reinterpret_cast<float4*>(y32 + r * ld32 + c) = f;
+      if (y16) *reinterpret_cast<uint2*>(y16 + r * ld16 + c) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
     } else {
-      for (int k = 0; k < n; ++k) v[k] = x[e + k];
-    }
-    long long rr = r;
-    for (int k = 0; k < n; ++k) {
-      if (c == C) { c = 0; ++rr; }
-      const float f = (float)v[k];
-      if (y32) y32[rr * ld32 + c] = f;
-      if (y16) y16[rr * ld16 + c] = __float2bfloat16_rn(f);
-      ++c;
+      const float f = (float)x[r * C + c];
+      if (y32) y32[r * ld32 + c] = f;
+      if (y16) y16[r * ld16 + c] = __float2bfloat16_rn(f);
     }
   }
 }
@@ -960,8 +959,10 @@ extern "C" int mmfm_u8_expand(const unsigned char* x, long long R, int C, float*
                               long long ld16, void* stream) {
   MMFM_REQUIRE(x && (y32 || y16) && R > 0 && C > 0, "mmfm_u8_expand: bad arguments");
   MMFM_REQUIRE((!y32 || ld32 >= C) && (!y16 || ld16 >= C), "mmfm_u8_expand: row pitch smaller than the row");
-  const long long total = R * (long long)C;
-  u8_expand_kernel<<<ew_grid(total / 16 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, total, C, y32, ld32, (bf16*)y16, ld16);
+  const bool vec = C % 4 == 0 && ld32 % 4 == 0 && ld16 % 4 == 0 && ((uintptr_t)x & 3) == 0 && ((uintptr_t)y32 & 15) == 0 &&
+                   ((uintptr_t)y16 & 7) == 0;
+  if (vec) u8_expand_kernel<true><<<ew_grid(R * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, R, C, y32, ld32, (bf16*)y16, ld16);
+  else u8_expand_kernel<false><<<ew_grid(R * (long long)C, 256), 256, 0, (cudaStream_t)stream>>>(x, R, C, y32, ld32, (bf16*)y16, ld16);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
