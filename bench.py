@@ -523,6 +523,9 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if ddp is not None:
+            ddp.close()
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

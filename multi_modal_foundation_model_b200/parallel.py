@@ -68,6 +68,25 @@ class DataParallel:
         if broadcast and self.world > 1:
             dist.broadcast(eng.store.flat, src=0, group=process_group)   # same initial weights on every rank
         self._plans = {}
+        self._graphs = {}
+        import atexit
+        import os
+        import weakref
+        self.graph_ddp = os.environ.get("MMFM_DDP_GRAPH", "1") != "0"
+        # captured graphs hold NCCL work: they must be gone before the process group is torn down.  Call close() before
+        # dist.destroy_process_group(); the exit hook covers a plain interpreter exit.
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref().close())
+
+    def close(self) -> None:
+        """Drop the captured graphs (they hold NCCL work) -- call before ``destroy_process_group``."""
+        if not self._graphs:
+            return
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
 
     def _segments(self, pl):
         key = id(pl)
@@ -83,6 +102,31 @@ class DataParallel:
         return seg
 
     def run_backward(self, pl) -> None:
+        """Backward schedule with the bucket all-reduces enqueued at their completion marks.  The first call per plan
+        runs eagerly (NCCL communicator set-up, kernel attributes); afterwards the whole sequence -- kernels, per-bucket
+        scaling and the NCCL all-reduces on their side stream -- is captured once into a CUDA graph and replayed, so the
+        multi-GPU step has the same launch-gap-free backward as the single-GPU one."""
+        st = self._graphs.get(id(pl))
+        if st is None:
+            st = self._graphs[id(pl)] = {"runs": 0, "graph": None}
+        if self.eng.use_graphs and self.graph_ddp and st["graph"] is None and st["runs"] >= 1 and self.world > 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_backward_eager(pl)
+                st["graph"] = g
+            except Exception:          # capture of collectives unsupported in this build: stay eager, loudly once
+                import warnings
+                warnings.warn("mmfm DataParallel: CUDA-graph capture of the backward + all-reduce failed; running eagerly")
+                self.graph_ddp = False
+                torch.cuda.synchronize()
+        st["runs"] += 1
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            self._run_backward_eager(pl)
+
+    def _run_backward_eager(self, pl) -> None:
         from . import ops
         n_calls, buckets = self._segments(pl)
         grad = self.eng.store.grad

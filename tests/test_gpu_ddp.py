@@ -21,8 +21,8 @@ def _worker(rank, world, port, out_dir):
     try:
         torch.manual_seed(100 + rank)            # different init per rank: the wrapper must broadcast rank 0's
         model = build_model(40, 2, small_config()).cuda().eval()
-        DataParallel(model, bucket_mb=0.25)      # small buckets -> several all-reduces inside backward
-        for step in range(2):                    # second step runs the CUDA-graph forward + eager bucketed backward
+        ddp = DataParallel(model, bucket_mb=0.25)   # small buckets -> several all-reduces inside backward
+        for step in (0, 2, 1):                   # eager, graph capture (backward + all-reduces), graph replay
             batch = make_batch(4, 40, 2, 100, step=10 * step + rank, pad_bins=5)
             md = make_mod_dict(batch, ["ap", "behavior"], "encoding" if step == 0 else "decoding", device="cuda")
             model.zero_grad(set_to_none=True)
@@ -32,6 +32,7 @@ def _worker(rank, world, port, out_dir):
         grads = {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
         weights = {n: p.detach().cpu().clone() for n, p in model.named_parameters()}
         torch.save({"grads": grads, "weights": weights}, os.path.join(out_dir, f"rank{rank}.pt"))
+        ddp.close()
     finally:
         dist.destroy_process_group()
 
