@@ -770,982 +770,16 @@ __global__ void __launch_bounds__(kAttnThreads, D == 32 ? 3 : 2) attn_bwd_dkv_ke
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// forward, tcgen05 / TMEM variant for Sk <= 256 (the model's S = n_mod * T = 200): the whole key range is one tile,
-// so the softmax is a single exact pass and the kernel is:
-//   TMA (Q 128 x D, K Npad x D, V Npad x D, swizzled)  ->  tcgen05.mma  S[128, Npad] = Q K^T  (fp32 in TMEM)
-//   4 warps, THREAD = QUERY ROW (TMEM lane): tcgen05.ld the row in 32-column chunks, mask from a per-chunk 32-bit
-//   word (key-validity bits | diagonal bit / causal prefix), max, exp2, sum, dropout on the packed bf16 pairs,
-//   tcgen05.st of P (bf16, two K elements per 32-bit column) OVER the already-consumed part of S
-//   tcgen05.mma  O[128, D] = P (A operand read from TMEM) . V (MN-major smem operand)   ->  scale, output dropout, store
-// No quad shuffles, no online rescaling, ~3x fewer instructions per score element than the mma.sync kernel.
-// The dropout field and the stored keep words are bit-identical to the flash kernel's (same Philox calls), so the
-// mma.sync backward kernels consume them unchanged.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kTcFwdThreads = 256;   // 2 column groups x 128 rows
-
-template <int D, bool DROP>
-__global__ void __launch_bounds__(kTcFwdThreads) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                    const __grid_constant__ CUtensorMap tmK,
-                                                                    const __grid_constant__ CUtensorMap tmV,
-                                                                    const AttnParams p, int npad, int tmem_cols) {
-  constexpr uint32_t kRowBytes = D * 2;                    // 64 (64B swizzle) or 128 (128B swizzle)
-  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;        // UMMA smem-descriptor swizzle code
-  constexpr uint32_t kSbo = 8 * kRowBytes;                 // 8-row swizzle atom
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t ld_bar, s_bar, o_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t s_colbits[8];
-  __shared__ float s_red[2][128];   // per column group: row max, later row sum
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sK = sQ + 128 * kRowBytes, sV = sK + 256 * kRowBytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, grp = warp >> 2;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int mode = p.mask_mode;
-  const long long bh = (long long)(b * p.nh + h);
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(&ld_bar, 1);
-    mbar_init(&s_bar, 1);
-    mbar_init(&o_bar, 1);
-    fence_mbar_init();
-    // the operand tiles are requested before this CTA owns any tensor memory: a CTA that is resident but still
-    // waiting for TMEM columns already has its loads in flight, which hides their latency behind its predecessor
-    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((128 + 2 * npad) * kRowBytes));
-    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
-    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
-    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_slot, (uint32_t)tmem_cols);
-    tmem_relinquish();
-  }
-  {
-    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
-    const int j = warp * 32 + lane;   // 8 warps -> 8 words
-    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
-    const uint32_t m = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) s_colbits[warp] = m;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_wait(&ld_bar, 0);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k) {
-        const uint64_t da = make_smem_desc(sQ + k * 32, 16, kSbo, kLayout);
-        const uint64_t db = make_smem_desc(sK + k * 32, 16, kSbo, kLayout);
-        umma_bf16(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
-      }
-      umma_commit(&s_bar);
-    }
-    __syncwarp();
-  }
-
-  // ---------------- softmax: thread = (query row, column group); group g owns the 32-column chunks c = g, g+2, .. ----
-  const int row = quad * 32 + lane;
-  const int i = q0 + row;
-  const float sl2 = p.scale * kLog2e;
-  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const int nch = (npad + 31) >> 5;      // 32-column chunks
-  const int nkb = (p.Sk + kTile - 1) / kTile;
-  mbar_wait(&s_bar, 0);
-  tc_fence_after();
-
-  auto allowed_word = [&](int c) -> uint32_t {
-    uint32_t aw = s_colbits[c];
-    const int rel = i - 32 * c;
-    if (mode == MMFM_MASK_KEY_OR_DIAG) {
-      if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
-    } else if (mode == MMFM_MASK_CAUSAL) {
-      aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
-    }
-    return aw;
-  };
-
-  // group g owns the 64-column blocks kb = g, g+2, ..  (chunks 2kb, 2kb+1): one set of Philox calls per block
-  const int nblk = (nch + 1) >> 1;
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int kb = grp; kb < nblk; kb += 2) {
-#pragma unroll 1
-    for (int c = 2 * kb; c < min(2 * kb + 2, nch); ++c) {
-      uint32_t r[32];
-      tmem_ld32(t_row + 32u * c, r);
-      tmem_ld_wait();
-      const uint32_t aw = allowed_word(c);
-      if (aw == 0xFFFFFFFFu) {
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[k]), __uint_as_float(r[k + 1])));
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if ((aw >> k) & 1u) mx = fmaxf(mx, __uint_as_float(r[k]));
-      }
-    }
-  }
-  s_red[grp][row] = mx;
-  __syncthreads();
-  mx = fmaxf(s_red[0][row], s_red[1][row]);
-  __syncthreads();   // the buffer is reused for the row sums below
-  const float base = (mx == -INFINITY) ? 0.f : mx * sl2;
-  float l = 0.f;
-  unsigned long long seed_p = 0ull;
-  uint32_t thresh4 = 0;
-  if (DROP) {
-    seed_p = *p.drop_p.seed;
-    thresh4 = p.drop_p.thresh * 0x01010101u;
-  }
-  const unsigned long long prow = (unsigned long long)bh * p.Sq + i;
-#pragma unroll 1
-  for (int kb = grp; kb < nblk; kb += 2) {
-    uint32_t mw[4][4];   // keep byte-masks of this block: [quad lane ql][word]
-    if (DROP) {
-#pragma unroll
-      for (int ql = 0; ql < 4; ++ql) {
-        const uint4 w = pdrop_bytes(seed_p, p.drop_p.site, prow, (uint32_t)nkb, (uint32_t)kb, (uint32_t)ql);
-        mw[ql][0] = __vcmpgeu4(w.x, thresh4);
-        mw[ql][1] = __vcmpgeu4(w.y, thresh4);
-        mw[ql][2] = __vcmpgeu4(w.z, thresh4);
-        mw[ql][3] = __vcmpgeu4(w.w, thresh4);
-      }
-      if (i < p.Sq)
-        *reinterpret_cast<uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + kb) * 4) =
-            make_uint2(mask_bits16(mw[0]) | (mask_bits16(mw[1]) << 16), mask_bits16(mw[2]) | (mask_bits16(mw[3]) << 16));
-    }
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int c = 2 * kb + hf;
-      if (c < nch) {
-        uint32_t r[32];
-        tmem_ld32(t_row + 32u * c, r);
-        tmem_ld_wait();
-        const uint32_t aw = allowed_word(c);
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * t]), sl2, -base));
-          float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * t + 1]), sl2, -base));
-          if (aw != 0xFFFFFFFFu) {
-            if (!((aw >> (2 * t)) & 1u)) e0 = 0.f;
-            if (!((aw >> (2 * t + 1)) & 1u)) e1 = 0.f;
-          }
-          l += e0 + e1;
-          pk[t] = pack_bf16x2(e0, e1);
-        }
-        if (DROP) {
-          // pair t covers columns 32c + 2t, +1: n-tile n = 4*hf + t/4, quad lane ql = t%4 -> bytes 2n, 2n+1 of call ql:
-          // word 2*hf + t/8, half (t/4)&1
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const uint32_t word = mw[t & 3][2 * hf + (t >> 3)];
-            pk[t] &= ((t >> 2) & 1) ? __byte_perm(word, 0u, 0x3322u) : __byte_perm(word, 0u, 0x1100u);
-          }
-        }
-        tmem_st16(t_row + 32u * c, pk);   // in place: bf16 chunk c over the first 16 columns of fp32 chunk c
-      }
-    }
-  }
-  s_red[grp][row] = l;
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-  l = s_red[0][row] + s_red[1][row];
-
-  const uint32_t o_col = (uint32_t)npad;
-  if (warp == 0) {
-    if (elect_one()) {
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);   // A (TMEM) K-major, B = V MN-major
-      const int nks = npad >> 4;
-      for (int kk = 0; kk < nks; ++kk) {
-        const uint64_t db = make_smem_desc(sV + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout);
-        umma_bf16_ts(tmem_base + o_col, tmem_base + 32u * (kk >> 1) + 8u * (kk & 1), db, idesc, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&o_bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&o_bar, 0);
-  tc_fence_after();
-
-  // ---------------- epilogue: each group stores half of the O row ----------------
-  float inv = l > 0.f ? 1.0f / l : 0.f;
-  if (grp == 0 && i < p.Sq) p.lse[bh * p.Sq + i] = (l > 0.f) ? (base + log2f(l)) * kLn2 : -INFINITY;
-  if (DROP) inv *= p.drop_p.scale;
-  const bool drop_o = p.drop_o.thresh != 0u;
-  unsigned long long seed_o = 0ull;
-  if (drop_o) seed_o = *p.drop_o.seed;
-  const uint32_t gpr_o = (uint32_t)((p.nh * D + 15) >> 4);
-  // pull this thread's part of the O row out of tensor memory, release the columns for the next CTA, then store
-  uint32_t r[D / 32][16];
-#pragma unroll
-  for (int u = 0; u < D / 32; ++u) tmem_ld16(t_row + o_col + (uint32_t)(grp * (D / 2) + 16 * u), r[u]);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
-  if (i < p.Sq) {
-#pragma unroll
-    for (int u = 0; u < D / 32; ++u) {
-      const int cc = grp * (D / 2) + 16 * u;   // column inside the head
-      float v[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[u][k]) * inv;
-      const int col = h * D + cc;
-      if (drop_o) {
-        const uint4 w = drop_bytes16(seed_o, p.drop_o.site, (uint64_t)((long long)b * p.Sq + i), gpr_o, (uint32_t)(col >> 4));
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = drop_byte(w, k) < p.drop_o.thresh ? 0.f : v[k] * p.drop_o.scale;
-      }
-      bf16* dst = p.o + ((long long)b * p.Sq + i) * p.ldo + col;
-#pragma unroll
-      for (int k = 0; k < 16; k += 8)
-        *reinterpret_cast<uint4*>(dst + k) = make_uint4(pack_bf16x2(v[k], v[k + 1]), pack_bf16x2(v[k + 2], v[k + 3]),
-                                                        pack_bf16x2(v[k + 4], v[k + 5]), pack_bf16x2(v[k + 6], v[k + 7]));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// backward, tcgen05 / TMEM variant (Sq, Sk <= 256 and 2*Npad + accumulators <= 512 TMEM columns).  Two kernels with the
-// forward's structure, one per orientation, so no atomics and no transposed fragments:
-//   dq  : CTA = (b, h, 128 queries).  S = Q K^T and dP = dO V^T land side by side in TMEM; 512 threads (row = TMEM lane,
-//         4 column groups) turn them into dS = P * (keep * dP - delta) and write it back IN PLACE as bf16 (chunk c of
-//         32 fp32 columns -> its own first 16 columns), which the next tcgen05.mma reads as its A operand:
-//         dQ = dS . K  (K tile re-used as MN-major B operand).
-//   dkv : CTA = (b, h, 128 keys).  S^T = K Q^T, dP^T = V dO^T; the threads (row = key) produce dS^T and P_drop^T in
-//         place; dK = dS^T . Q and dV = P_drop^T . dO re-use the Q / dO tiles as MN-major B operands.
-// lse / delta / keep bits come from the forward and the prep kernel exactly as in the mma.sync path.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kTcBwdThreads = 512;
-
-template <int D, bool DROP>
-__global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dq_tc_kernel(
-    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npad) {
-  constexpr uint32_t kRowBytes = D * 2;
-  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;
-  constexpr uint32_t kSbo = 8 * kRowBytes;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t ld_bar, m1_bar, m2_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t s_colbits[8];
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sdO = sQ + 128 * kRowBytes, sK = sdO + 128 * kRowBytes, sV = sK + 256 * kRowBytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, grp = warp >> 2;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int mode = p.mask_mode;
-  const long long bh = (long long)(b * p.nh + h);
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(&ld_bar, 1);
-    mbar_init(&m1_bar, 1);
-    mbar_init(&m2_bar, 1);
-    fence_mbar_init();
-    // loads first, tensor memory second (see the forward kernel)
-    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npad) * kRowBytes));
-    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq + q0);
-    tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq + q0);
-    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk);
-    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk);
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_slot, 512u);
-    tmem_relinquish();
-  }
-  if (warp >= 8) {
-    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
-    const int w = warp - 8;
-    const int j = w * 32 + lane;
-    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
-    const uint32_t m = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) s_colbits[w] = m;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  const uint32_t dp_col = (uint32_t)npad, acc_col = 2u * (uint32_t)npad;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_wait(&ld_bar, 0);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npad, 0, 0);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem_base, make_smem_desc(sQ + k * 32, 16, kSbo, kLayout), make_smem_desc(sK + k * 32, 16, kSbo, kLayout),
-                  idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem_base + dp_col, make_smem_desc(sdO + k * 32, 16, kSbo, kLayout),
-                  make_smem_desc(sV + k * 32, 16, kSbo, kLayout), idesc, k > 0 ? 1u : 0u);
-      umma_commit(&m1_bar);
-    }
-    __syncwarp();
-  }
-
-  const int row = quad * 32 + lane;
-  const int i = q0 + row;
-  const float sl2 = p.scale * kLog2e;
-  const float dsc = DROP ? p.drop_p.scale : 1.0f;
-  const float lse2 = (i < p.Sq) ? p.lse[bh * p.Sq + i] * kLog2e : INFINITY;
-  const float dl = ((i < p.Sq) ? p.delta[bh * p.Sq + i] : 0.f) / dsc;
-  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const int nch = (npad + 31) >> 5;
-  const int nkb = (p.Sk + kTile - 1) / kTile;
-  // keep words of this thread's (at most two) chunks, fetched while the loads / first MMAs are in flight
-  uint2 kpre[2] = {make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu)};
-  if (DROP && i < p.Sq) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = grp + 4 * u;
-      if (c < nch) kpre[u] = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
-    }
-  }
-  mbar_wait(&m1_bar, 0);
-  tc_fence_after();
-
-  // items = (chunk u, half hf): the TMEM loads of item n+1 are issued before item n is computed, so their latency is
-  // hidden behind the exp / select / pack work (tcgen05.wait::ld covers every outstanding load of the thread)
-  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
-  uint32_t rs[2][16], rd[2][16];
-  if (nmine > 0) {
-    tmem_ld16(t_row + 32u * grp, rs[0]);
-    tmem_ld16(t_row + dp_col + 32u * grp, rd[0]);
-    tmem_ld_wait();
-  }
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int c = grp + 4 * u;
-    if (u >= nmine) break;
-    uint32_t aw = s_colbits[c];
-    const int rel = i - 32 * c;
-    if (mode == MMFM_MASK_KEY_OR_DIAG) {
-      if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
-    } else if (mode == MMFM_MASK_CAUSAL) {
-      aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
-    }
-    uint32_t kw[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
-    if (DROP) {
-      const uint2 w2 = kpre[u];
-      const int sh = 8 * (c & 1);
-      kw[0] = (w2.x & 0xFFFFu) >> sh; kw[1] = (w2.x >> 16) >> sh;
-      kw[2] = (w2.y & 0xFFFFu) >> sh; kw[3] = (w2.y >> 16) >> sh;
-    }
-    uint32_t outp[16];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int cur = hf, nxt = hf ^ 1;
-      // prefetch the next item
-      if (hf == 0) {
-        tmem_ld16(t_row + 32u * c + 16u, rs[nxt]);
-        tmem_ld16(t_row + dp_col + 32u * c + 16u, rd[nxt]);
-      } else if (u + 1 < nmine) {
-        tmem_ld16(t_row + 32u * (c + 4), rs[nxt]);
-        tmem_ld16(t_row + dp_col + 32u * (c + 4), rd[nxt]);
-      }
-      float ds[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int kk = 16 * hf + k;                 // column inside the chunk
-        const bool ok = (aw >> kk) & 1u;
-        const float pe = fast_exp2(fmaf(__uint_as_float(rs[cur][k]), sl2, -lse2));
-        float dpe = __uint_as_float(rd[cur][k]);
-        if (DROP) {
-          // column jj = 32*(c&1) + kk of the 64-block: n = jj/8, ql = (jj%8)/2, e = jj%2 -> bit 2n+e (kw pre-shifted)
-          if (!((kw[(kk & 7) >> 1] >> (2 * (kk >> 3) + (kk & 1))) & 1u)) dpe = 0.f;
-        }
-        ds[k] = ok ? pe * (dpe - dl) : 0.f;   // masked columns may hold uninitialised TMEM bits: never multiply them
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) outp[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
-      tmem_ld_wait();
-    }
-    tmem_st16(t_row + 32u * c, outp);   // in place: bf16 chunk c over the first half of fp32 chunk c
-  }
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-
-  if (warp == 0) {
-    if (elect_one()) {
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-      const int nks = npad >> 4;
-      for (int kk = 0; kk < nks; ++kk) {
-        const uint64_t db = make_smem_desc(sK + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout);
-        umma_bf16_ts(tmem_base + acc_col, tmem_base + 32u * (kk >> 1) + 8u * (kk & 1), db, idesc, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&m2_bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&m2_bar, 0);
-  tc_fence_after();
-  uint32_t r[16];
-  if (16 * grp < D) {
-    tmem_ld16(t_row + acc_col + 16u * grp, r);
-    tmem_ld_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);   // columns go back before the global stores
-  if (16 * grp < D) {
-    if (i < p.Sq) {
-      const float fs = p.scale * dsc;
-      bf16* dst = p.dq + ((long long)b * p.Sq + i) * p.lddq + h * D + 16 * grp;
-#pragma unroll
-      for (int k = 0; k < 16; k += 8)
-        *reinterpret_cast<uint4*>(dst + k) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
-                       pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
-    }
-  }
-}
-
-template <int D, bool DROP>
-__global__ void __launch_bounds__(kTcBwdThreads, 1) attn_bwd_dkv_tc_kernel(
-    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npq) {
-  constexpr uint32_t kRowBytes = D * 2;
-  constexpr uint32_t kLayout = (D == 32) ? 4u : 2u;
-  constexpr uint32_t kSbo = 8 * kRowBytes;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t ld_bar, m1_bar, m2_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_lse[256];
-  __shared__ __align__(16) float s_dl[256];
-  __shared__ __align__(16) unsigned short s_keep[256][8];   // [query][2 key blocks of this tile][4 quad lanes]
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = sK + 128 * kRowBytes, sQ = sV + 128 * kRowBytes, sdO = sQ + 256 * kRowBytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, grp = warp >> 2;
-  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int mode = p.mask_mode;
-  const long long bh = (long long)(b * p.nh + h);
-  const int nkb = (p.Sk + kTile - 1) / kTile;
-  const float dsc = DROP ? p.drop_p.scale : 1.0f;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(&ld_bar, 1);
-    mbar_init(&m1_bar, 1);
-    mbar_init(&m2_bar, 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(&ld_bar, (uint32_t)((256 + 2 * npq) * kRowBytes));
-    tma_load_2d_addr(sK, &tmK, &ld_bar, h * D, b * p.Sk + k0);
-    tma_load_2d_addr(sV, &tmV, &ld_bar, h * D, b * p.Sk + k0);
-    tma_load_2d_addr(sQ, &tmQ, &ld_bar, h * D, b * p.Sq);
-    tma_load_2d_addr(sdO, &tmdO, &ld_bar, h * D, b * p.Sq);
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_slot, 512u);
-    tmem_relinquish();
-  }
-  if (tid < 256) {
-    const int qi = tid;
-    const bool ok = qi < p.Sq;
-    s_lse[qi] = ok ? p.lse[bh * p.Sq + qi] * kLog2e : INFINITY;
-    s_dl[qi] = ok ? p.delta[bh * p.Sq + qi] / dsc : 0.f;
-    if (DROP) {
-      const int kb0 = k0 / kTile;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        uint2 w2 = make_uint2(0u, 0u);
-        if (ok && kb0 + u < nkb) w2 = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + qi) * nkb + kb0 + u) * 4);
-        *reinterpret_cast<uint2*>(&s_keep[qi][4 * u]) = w2;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  const uint32_t dp_col = (uint32_t)npq, acc_col = 2u * (uint32_t)npq;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_wait(&ld_bar, 0);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)npq, 0, 0);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem_base, make_smem_desc(sK + k * 32, 16, kSbo, kLayout), make_smem_desc(sQ + k * 32, 16, kSbo, kLayout),
-                  idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem_base + dp_col, make_smem_desc(sV + k * 32, 16, kSbo, kLayout),
-                  make_smem_desc(sdO + k * 32, 16, kSbo, kLayout), idesc, k > 0 ? 1u : 0u);
-      umma_commit(&m1_bar);
-    }
-    __syncwarp();
-  }
-
-  const int row = quad * 32 + lane;   // key row of the tile
-  const int j = k0 + row;
-  const bool rowvalid = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || p.key_valid[(long long)b * p.Sk + j] != 0);
-  const float sl2 = p.scale * kLog2e;
-  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const int nch = (npq + 31) >> 5;
-  // keep-bit address of this key inside a query's 8-word row: word 4*(row/64) + (row%8)/2, bit 2*((row%64)/8) + row%2
-  const int kword = 4 * (row >> 6) + ((row & 7) >> 1);
-  const int kbit = 2 * ((row & 63) >> 3) + (row & 1);
-  mbar_wait(&m1_bar, 0);
-  tc_fence_after();
-
-  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
-  uint32_t rs[2][16], rd[2][16];
-  if (nmine > 0) {
-    tmem_ld16(t_row + 32u * grp, rs[0]);
-    tmem_ld16(t_row + dp_col + 32u * grp, rd[0]);
-    tmem_ld_wait();
-  }
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int c = grp + 4 * u;
-    if (u >= nmine) break;
-    // allowed(query i = 32c + k, key j)
-    const int ncol = p.Sq - 32 * c;
-    uint32_t aw = ncol >= 32 ? 0xFFFFFFFFu : (ncol <= 0 ? 0u : ((1u << ncol) - 1u));   // queries in range
-    const int rel = j - 32 * c;                                                        // column where i == j
-    if (mode == MMFM_MASK_CAUSAL) {
-      aw &= (rel <= 0) ? 0xFFFFFFFFu : (rel >= 32 ? 0u : ~((1u << rel) - 1u));          // i >= j
-      if (j >= p.Sk) aw = 0u;
-    } else {
-      const uint32_t inr = aw;
-      if (!rowvalid) aw = 0u;
-      if (mode == MMFM_MASK_KEY_OR_DIAG && rel >= 0 && rel < 32 && j < p.Sk) aw |= (1u << rel) & inr;
-    }
-    uint32_t outs[16], outp[16];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int cur = hf, nxt = hf ^ 1;
-      if (hf == 0) {   // prefetch the next item's TMEM columns (see the dq kernel)
-        tmem_ld16(t_row + 32u * c + 16u, rs[nxt]);
-        tmem_ld16(t_row + dp_col + 32u * c + 16u, rd[nxt]);
-      } else if (u + 1 < nmine) {
-        tmem_ld16(t_row + 32u * (c + 4), rs[nxt]);
-        tmem_ld16(t_row + dp_col + 32u * (c + 4), rd[nxt]);
-      }
-      float ds[16], pd[16];
-#pragma unroll
-      for (int k4 = 0; k4 < 16; k4 += 4) {
-        const int qi = 32 * c + 16 * hf + k4;
-        const float4 l4 = *reinterpret_cast<const float4*>(&s_lse[qi]);
-        const float4 d4 = *reinterpret_cast<const float4*>(&s_dl[qi]);
-        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
-          const int k = k4 + uu, kk = 16 * hf + k;
-          const bool ok = (aw >> kk) & 1u;
-          const float pe = fast_exp2(fmaf(__uint_as_float(rs[cur][k]), sl2, -lv[uu]));
-          float dpe = __uint_as_float(rd[cur][k]);
-          float pde = pe;
-          if (DROP) {
-            const uint32_t w = s_keep[qi + uu][kword];
-            if (!((w >> kbit) & 1u)) { dpe = 0.f; pde = 0.f; }
-          }
-          ds[k] = ok ? pe * (dpe - dv[uu]) : 0.f;   // masked columns may hold uninitialised TMEM bits
-          pd[k] = ok ? pde : 0.f;
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        outs[8 * hf + t] = pack_bf16x2(ds[2 * t], ds[2 * t + 1]);
-        outp[8 * hf + t] = pack_bf16x2(pd[2 * t], pd[2 * t + 1]);
-      }
-      tmem_ld_wait();
-    }
-    tmem_st16(t_row + 32u * c, outs);
-    tmem_st16(t_row + dp_col + 32u * c, outp);
-  }
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-
-  if (warp == 0) {
-    if (elect_one()) {
-      tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, D, 0, 1);
-      const int nks = npq >> 4;
-      for (int kk = 0; kk < nks; ++kk) {
-        const uint32_t a_off = 32u * (kk >> 1) + 8u * (kk & 1);
-        umma_bf16_ts(tmem_base + acc_col, tmem_base + a_off,
-                     make_smem_desc(sQ + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc, kk > 0 ? 1u : 0u);
-        umma_bf16_ts(tmem_base + acc_col + D, tmem_base + dp_col + a_off,
-                     make_smem_desc(sdO + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc, kk > 0 ? 1u : 0u);
-      }
-      umma_commit(&m2_bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(&m2_bar, 0);
-  tc_fence_after();
-  // 2*D accumulator columns (dK | dV) in 16-column pieces over the 4 thread groups; tensor memory is released
-  // before the global stores
-  constexpr int kPieces = (2 * D) / 16, kPer = kPieces / 4;
-  uint32_t r[kPer][16];
-#pragma unroll
-  for (int u = 0; u < kPer; ++u) tmem_ld16(t_row + acc_col + 16u * (grp + 4 * u), r[u]);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
-  if (j < p.Sk) {
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int piece = grp + 4 * u;
-      const bool is_dv = 16 * piece >= D;
-      const int col = 16 * piece - (is_dv ? D : 0);
-      const float fs = is_dv ? dsc : p.scale * dsc;
-      bf16* dst = (is_dv ? p.dv + ((long long)b * p.Sk + j) * p.lddv : p.dk + ((long long)b * p.Sk + j) * p.lddk) + h * D + col;
-#pragma unroll
-      for (int k = 0; k < 16; k += 8)
-        *reinterpret_cast<uint4*>(dst + k) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[u][k]) * fs, __uint_as_float(r[u][k + 1]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 2]) * fs, __uint_as_float(r[u][k + 3]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 4]) * fs, __uint_as_float(r[u][k + 5]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 6]) * fs, __uint_as_float(r[u][k + 7]) * fs));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// backward, fused tcgen05 variant (d_head = 32, Sq, Sk <= 256): ONE CTA per (batch, head) computes dQ, dK and dV, so
-// every score element goes through the softmax / dropout / dS arithmetic once instead of once per orientation.
-// Per 128-query tile:
-//   MMA  S  = Q K^T                       -> TMEM [0, Npad)
-//   A    thread = (query row, column group): p = exp2(s*scale - lse) under the mask; P_drop (bf16) -> smem slabs;
-//        p stays in registers as packed bf16
-//   MMA  dP = dO V^T                      -> TMEM [0, Npad) (S is dead);   dV += P_drop^T dO   (A = slabs read MN-major)
-//   B    dS = p * (keep * dP - delta)     -> smem slabs
-//   MMA  dQ = dS K (A = slabs read K-major);  dK += dS^T Q (same slabs read MN-major)
+// backward, fused + software-pipelined tcgen05 kernel (d_head = 32, Sq, Sk <= 256): ONE CTA per (batch, head) computes
+// dQ, dK and dV, so every score element goes through the softmax / dropout / dS arithmetic once.  This is the
+// non-persistent form of attention_bwd_persist.cu (used when the side data are not 16-byte aligned, Sq % 4 != 0):
+//   pass A  thread = (query row, column group): p = exp2(s*scale - lse) under the mask; P_drop (bf16) -> smem slabs;
+//           p and p*keep stay in registers as packed bf16
+//   pass B  dS = p_drop * dP - p * delta -> smem slabs
 // The slabs are the canonical 128-byte-swizzled layout ([128 query rows] x [64 keys] per slab), written with 16-byte
-// stores from registers, so one copy of dS serves both the dQ (K-major A) and the dK (MN-major A) products.  dK / dV
-// accumulate in TMEM across the query tiles and are stored once at the end.
-// ------------------------------------------------------------------------------------------------------------
-template <bool DROP>
-__global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_fused_tc_kernel(
-    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int npad) {
-  constexpr int D = 32;
-  constexpr uint32_t kRowBytes = 64, kSbo64 = 512;   // operand tiles: [rows][32 bf16], 64-byte swizzle
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t ld_kv_bar, ld_q_bar, s_bar, dp_bar, mm_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ uint32_t s_colbits[8];
-
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = smem_base, sV = sK + 256 * kRowBytes, sQ = sV + 256 * kRowBytes, sdO = sQ + 128 * kRowBytes;
-  const uint32_t sdS = sdO + 128 * kRowBytes, sPd = sdS + 4 * kSlabBytes;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, grp = warp >> 2;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int mode = p.mask_mode;
-  const long long bh = (long long)(b * p.nh + h);
-  const int nqt = (p.Sq + 127) >> 7;
-  const int nkt = (npad + 127) >> 7;   // 128-key M tiles of dK / dV
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(&ld_kv_bar, 1);
-    mbar_init(&ld_q_bar, 1);
-    mbar_init(&s_bar, 1);
-    mbar_init(&dp_bar, 1);
-    mbar_init(&mm_bar, 1);
-    fence_mbar_init();
-    mbar_arrive_expect_tx(&ld_kv_bar, (uint32_t)(2 * npad * kRowBytes));
-    tma_load_2d_addr(sK, &tmK, &ld_kv_bar, h * D, b * p.Sk);
-    tma_load_2d_addr(sV, &tmV, &ld_kv_bar, h * D, b * p.Sk);
-    mbar_arrive_expect_tx(&ld_q_bar, (uint32_t)(256 * kRowBytes));
-    tma_load_2d_addr(sQ, &tmQ, &ld_q_bar, h * D, b * p.Sq);
-    tma_load_2d_addr(sdO, &tmdO, &ld_q_bar, h * D, b * p.Sq);
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_slot, 512u);
-    tmem_relinquish();
-  }
-  if (warp >= 8) {
-    const unsigned char* kvg = p.key_valid + (long long)b * p.Sk;
-    const int w = warp - 8;
-    const int j = w * 32 + lane;
-    const bool v = (j < p.Sk) && (mode == MMFM_MASK_CAUSAL || kvg[j] != 0);
-    const uint32_t m = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) s_colbits[w] = m;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
-  const uint32_t dq_col = (uint32_t)npad, dk_col = dq_col + 32u, dv_col = dk_col + 64u;
-
-  const int row = quad * 32 + lane;
-  const float sl2 = p.scale * kLog2e;
-  const float dsc = DROP ? p.drop_p.scale : 1.0f;
-  const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-  const int nch = (npad + 31) >> 5;
-  const int nkb = (p.Sk + kTile - 1) / kTile;
-  const int nmine = (grp < nch ? 1 : 0) + (grp + 4 < nch ? 1 : 0);
-  const uint32_t idesc_s = make_idesc_bf16(128, (uint32_t)npad, 0, 0);   // S / dP: both operands K-major
-  const uint32_t idesc_q = make_idesc_bf16(128, D, 0, 1);                // dQ: A K-major (slabs), B MN-major (K tile)
-  const uint32_t idesc_t = make_idesc_bf16(128, D, 1, 1);                // dK / dV: A MN-major (slabs), B MN-major
-
-#pragma unroll 1
-  for (int qt = 0; qt < nqt; ++qt) {
-    const uint32_t par = (uint32_t)(qt & 1);
-    const int q0 = qt * 128;
-    const int i = q0 + row;
-    if (warp == 0) {
-      if (elect_one()) {
-        if (qt == 0) mbar_wait(&ld_kv_bar, 0);
-        mbar_wait(&ld_q_bar, par);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16(tmem_base, make_smem_desc(sQ + k * 32, 16, kSbo64, 4), make_smem_desc(sK + k * 32, 16, kSbo64, 4),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&s_bar);
-      }
-      __syncwarp();
-    }
-    const float lse2 = (i < p.Sq) ? p.lse[bh * p.Sq + i] * kLog2e : INFINITY;
-    const float dl = ((i < p.Sq) ? p.delta[bh * p.Sq + i] : 0.f) / dsc;
-    uint2 kpre[2] = {make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu), make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu)};
-    if (DROP && i < p.Sq) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = grp + 4 * u;
-        if (c < nch) kpre[u] = *reinterpret_cast<const uint2*>(p.p_keep + ((bh * p.Sq + i) * nkb + (c >> 1)) * 4);
-      }
-    }
-    uint32_t aws[2] = {0u, 0u};
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = grp + 4 * u;
-      if (c < nch) {
-        uint32_t aw = s_colbits[c];
-        const int rel = i - 32 * c;
-        if (mode == MMFM_MASK_KEY_OR_DIAG) {
-          if (rel >= 0 && rel < 32 && i < p.Sk) aw |= 1u << rel;
-        } else if (mode == MMFM_MASK_CAUSAL) {
-          aw &= (rel >= 31) ? 0xFFFFFFFFu : (rel < 0 ? 0u : ((2u << rel) - 1u));
-        }
-        aws[u] = aw;
-      }
-    }
-    mbar_wait(&s_bar, par);
-    tc_fence_after();
-
-    // ---------------- pass A: probabilities ----------------
-    uint32_t pk[2][16];    // p as packed bf16, kept for pass B
-    uint32_t pdq[2][16];   // p * keep as packed bf16, kept for pass B (dS = p_drop * dP - p * delta)
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u >= nmine) break;
-      const int c = grp + 4 * u;
-      const uint32_t aw = aws[u];
-      uint32_t km[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
-      if (DROP) {
-        const uint2 w2 = kpre[u];
-        const int sh = 8 * (c & 1);   // second 32-column chunk of the 64-key block: n-tiles 4..7 -> bits 8..15
-        keep_msb_words((w2.x & 0xFFFFu) >> sh, km[0]);
-        keep_msb_words((w2.x >> 16) >> sh, km[1]);
-        keep_msb_words((w2.y & 0xFFFFu) >> sh, km[2]);
-        keep_msb_words((w2.y >> 16) >> sh, km[3]);
-      }
-      const bool masked = __any_sync(0xffffffffu, aw != 0xFFFFFFFFu);
-      uint32_t rs[2][16];
-      tmem_ld16(t_row + 32u * c, rs[0]);
-      tmem_ld16(t_row + 32u * c + 16u, rs[1]);
-      tmem_ld_wait();
-      uint32_t pdk[2][8];
-      if (masked) {
-        bwd_prob_half<true, DROP, 0>(rs[0], aw, sl2, lse2, km, &pk[u][0], pdk[0]);
-        bwd_prob_half<true, DROP, 1>(rs[1], aw, sl2, lse2, km, &pk[u][8], pdk[1]);
-      } else {
-        bwd_prob_half<false, DROP, 0>(rs[0], aw, sl2, lse2, km, &pk[u][0], pdk[0]);
-        bwd_prob_half<false, DROP, 1>(rs[1], aw, sl2, lse2, km, &pk[u][8], pdk[1]);
-      }
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-        for (int t = 0; t < 8; ++t) pdq[u][8 * hf + t] = pdk[hf][t];
-        // two 16-byte pieces (8 keys each) of this row into the P_drop slab
-#pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-          const int j16 = (c & 1) * 4 + hf * 2 + q4;
-          const uint32_t addr = sPd + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
-          st_shared_v4(addr, pdk[hf][4 * q4], pdk[hf][4 * q4 + 1], pdk[hf][4 * q4 + 2], pdk[hf][4 * q4 + 3]);
-        }
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-
-    if (warp == 0) {
-      if (elect_one()) {
-        tc_fence_after();
-        // dP = dO V^T over the dead S columns
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16(tmem_base, make_smem_desc(sdO + k * 32, 16, kSbo64, 4), make_smem_desc(sV + k * 32, 16, kSbo64, 4),
-                    idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&dp_bar);
-        // dV[key tile mt] += P_drop^T[keys, queries] . dO[queries, d]
-        for (int mt = 0; mt < nkt; ++mt)
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem_base + dv_col + 32u * mt,
-                      make_smem_desc(sPd + (uint32_t)(2 * mt) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
-                      make_smem_desc(sdO + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_t,
-                      (qt > 0 || kk > 0) ? 1u : 0u);
-      }
-      __syncwarp();
-    }
-    mbar_wait(&dp_bar, par);
-    tc_fence_after();
-
-    // ---------------- pass B: dS ----------------
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u >= nmine) break;
-      const int c = grp + 4 * u;
-      const uint32_t aw = aws[u];
-      const bool masked = __any_sync(0xffffffffu, aw != 0xFFFFFFFFu);
-      uint32_t rd[2][16];
-      tmem_ld16(t_row + 32u * c, rd[0]);
-      tmem_ld16(t_row + 32u * c + 16u, rd[1]);
-      tmem_ld_wait();
-      uint32_t dsk[2][8];
-      if (masked) {
-        bwd_ds_half<true>(rd[0], aw & 0xFFFFu, dl, &pk[u][0], &pdq[u][0], dsk[0]);
-        bwd_ds_half<true>(rd[1], aw >> 16, dl, &pk[u][8], &pdq[u][8], dsk[1]);
-      } else {
-        bwd_ds_half<false>(rd[0], 0xFFFFu, dl, &pk[u][0], &pdq[u][0], dsk[0]);
-        bwd_ds_half<false>(rd[1], 0xFFFFu, dl, &pk[u][8], &pdq[u][8], dsk[1]);
-      }
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-          const int j16 = (c & 1) * 4 + hf * 2 + q4;
-          const uint32_t addr = sdS + (uint32_t)(c >> 1) * kSlabBytes + (uint32_t)row * 128u + (uint32_t)((j16 ^ (row & 7)) * 16);
-          st_shared_v4(addr, dsk[hf][4 * q4], dsk[hf][4 * q4 + 1], dsk[hf][4 * q4 + 2], dsk[hf][4 * q4 + 3]);
-        }
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-
-    if (warp == 0) {
-      if (elect_one()) {
-        tc_fence_after();
-        // dQ = dS . K
-        const int nks = npad >> 4;
-        for (int kk = 0; kk < nks; ++kk)
-          umma_bf16(tmem_base + dq_col,
-                    make_smem_desc(sdS + (uint32_t)(kk >> 2) * kSlabBytes + (uint32_t)(kk & 3) * 32u, 16, 1024, 2),
-                    make_smem_desc(sK + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_q, kk > 0 ? 1u : 0u);
-        // dK[key tile mt] += dS^T . Q
-        for (int mt = 0; mt < nkt; ++mt)
-          for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(tmem_base + dk_col + 32u * mt,
-                      make_smem_desc(sdS + (uint32_t)(2 * mt) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
-                      make_smem_desc(sQ + (uint32_t)kk * 16u * kRowBytes, kSbo64, kSbo64, 4), idesc_t,
-                      (qt > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&mm_bar);
-      }
-      __syncwarp();
-    }
-    mbar_wait(&mm_bar, par);
-    tc_fence_after();
-    // every MMA that reads the Q / dO tiles and the slabs has finished: fetch the next query tile
-    if (tid == 0 && qt + 1 < nqt) {
-      mbar_arrive_expect_tx(&ld_q_bar, (uint32_t)(256 * kRowBytes));
-      tma_load_2d_addr(sQ, &tmQ, &ld_q_bar, h * D, b * p.Sq + q0 + 128);
-      tma_load_2d_addr(sdO, &tmdO, &ld_q_bar, h * D, b * p.Sq + q0 + 128);
-    }
-    if (grp < 2) {
-      uint32_t r[16];
-      tmem_ld16(t_row + dq_col + 16u * grp, r);
-      tmem_ld_wait();
-      if (i < p.Sq) {
-        const float fs = p.scale * dsc;
-        bf16* dst = p.dq + ((long long)b * p.Sq + i) * p.lddq + h * D + 16 * grp;
-#pragma unroll
-        for (int k = 0; k < 16; k += 8)
-          *reinterpret_cast<uint4*>(dst + k) =
-              make_uint4(pack_bf16x2(__uint_as_float(r[k]) * fs, __uint_as_float(r[k + 1]) * fs),
-                         pack_bf16x2(__uint_as_float(r[k + 2]) * fs, __uint_as_float(r[k + 3]) * fs),
-                         pack_bf16x2(__uint_as_float(r[k + 4]) * fs, __uint_as_float(r[k + 5]) * fs),
-                         pack_bf16x2(__uint_as_float(r[k + 6]) * fs, __uint_as_float(r[k + 7]) * fs));
-      }
-    }
-    tc_fence_before();   // the dQ columns are rewritten by the next tile's MMA (ordered by the barriers of pass A)
-  }
-
-  // ---------------- dK / dV: TMEM lane = key row of the tile ----------------
-  // pieces: (mt, which, half) -> 16 columns; 4 * nkt pieces over the 4 thread groups
-  uint32_t r[2][16];
-  int npiece = 0;
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int piece = grp + 4 * u;          // mt = piece / 4, which = (piece / 2) & 1 (0 dK, 1 dV), half = piece & 1
-    if (piece < 4 * nkt) {
-      const int mt = piece >> 2, which = (piece >> 1) & 1, half = piece & 1;
-      tmem_ld16(t_row + (which ? dv_col : dk_col) + 32u * mt + 16u * half, r[u]);
-      npiece = u + 1;
-    }
-  }
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    if (u >= npiece) break;
-    const int piece = grp + 4 * u;
-    const int mt = piece >> 2, which = (piece >> 1) & 1, half = piece & 1;
-    const int j = mt * 128 + row;
-    if (j < p.Sk) {
-      const float fs = which ? dsc : p.scale * dsc;
-      bf16* dst = (which ? p.dv + ((long long)b * p.Sk + j) * p.lddv : p.dk + ((long long)b * p.Sk + j) * p.lddk) + h * D + 16 * half;
-#pragma unroll
-      for (int k = 0; k < 16; k += 8)
-        *reinterpret_cast<uint4*>(dst + k) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[u][k]) * fs, __uint_as_float(r[u][k + 1]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 2]) * fs, __uint_as_float(r[u][k + 3]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 4]) * fs, __uint_as_float(r[u][k + 5]) * fs),
-                       pack_bf16x2(__uint_as_float(r[u][k + 6]) * fs, __uint_as_float(r[u][k + 7]) * fs));
-    }
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------
-// backward, fused + software-pipelined tcgen05 variant (d_head = 32, Sq, Sk <= 256).  Same data flow as
-// attn_bwd_fused_tc_kernel, but the key range is split into two 128-key halves with their own S / dP buffer in TMEM
-// (columns [0,128) and [128,256)) and their own barriers, and the passes run in the order  A(h0) A(h1) B(h0) B(h1)
-// per query tile.  Every MMA batch is issued right after the pass that produces its operands and is waited for one
+// stores from registers, so one copy of dS serves both the dQ (K-major A) and the dK (MN-major A) products.
+// The key range is split into two 128-key halves with their own S / dP buffer in TMEM (columns [0,128) and [128,256))
+// and their own barriers, and the passes run in the order  A(h0) A(h1) B(h0) B(h1) per query tile.  Every MMA batch is issued right after the pass that produces its operands and is waited for one
 // pass later, so the threads never sit on a tensor-pipe round trip:
 //   after A(h):  dP_h = dO V_h^T (over the dead S_h) ; dV_h += P_drop_h^T dO
 //   after B(h):  dQ += dS_h K_h ; dK_h += dS_h^T Q ; S_h of the NEXT query tile
@@ -2179,54 +1213,35 @@ static AttnParams to_params(const mmfm_attn_args* a) {
     }                                                                                             \
   } while (0)
 
-template <int D>
-static int launch_fwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
-  const int npad = (a->Sk + 15) / 16 * 16;
-  int tmem_cols = 32;
-  while (tmem_cols < npad + D) tmem_cols *= 2;
-  const TmaSwizzle sw = (D == 32) ? TMA_SW_64 : TMA_SW_128;
-  CUtensorMap tq, tk, tv;
-  const uint64_t width = (uint64_t)a->n_heads * D;
-  if (int rc = make_tmap_bf16_2d(&tq, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, 128, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npad, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npad, sw)) return rc;
-  const int smem = 1024 + (128 + 2 * 256) * D * 2;
-  const bool drop = a->drop_p.thresh != 0u;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[drop]) {
-    if (drop) MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[drop] = true;
+// MMFM_ATTN_TC=0 forces the mma.sync kernels everywhere (A/B measurements)
+static bool attn_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMFM_ATTN_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
   }
-  dim3 grid((a->Sq + 127) / 128, a->n_heads, a->B);
-  if (drop) attn_fwd_tc_kernel<D, true><<<grid, kTcFwdThreads, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
-  else attn_fwd_tc_kernel<D, false><<<grid, kTcFwdThreads, smem, st>>>(tq, tk, tv, p, npad, tmem_cols);
-  MMFM_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return v != 0;
+}
+static bool env_on(const char* name, int* cache) {   // default on; "<name>=0" switches a kernel family off
+  if (*cache < 0) {
+    const char* e = getenv(name);
+    *cache = (e && e[0] == '0') ? 0 : 1;
+  }
+  return *cache != 0;
 }
 
-static bool g_attn_tc = true;   // MMFM_ATTN_TC=0 forces the mma.sync forward (A/B measurements)
-
+// Forward dispatch:
+//   no modality-separation mask, 16-byte aligned operands -> persistent warp-specialised tcgen05 kernel (attention_pipe.cu)
+//   otherwise                                             -> mma.sync flash kernel (modality ids, odd alignments)
 extern "C" int mmfm_attention_fwd(const mmfm_attn_args* a, void* stream) {
   if (int rc = check_common(a, "mmfm_attention_fwd")) return rc;
   const bool drop = a->drop_p.thresh != 0u, sep = a->mod_q != nullptr;
   const AttnParams p = to_params(a);
-  static bool env_read = false;
-  if (!env_read) {
-    const char* e = getenv("MMFM_ATTN_TC");
-    if (e && e[0] == '0') g_attn_tc = false;
-    env_read = true;
-  }
   const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
                       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->o)) & 15) == 0;
-  static int pipe = -1;   // MMFM_ATTN_PIPE=0 falls back to the one-CTA-per-tile forward kernels (A/B measurements)
-  if (pipe < 0) {
-    const char* e = getenv("MMFM_ATTN_PIPE");
-    pipe = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (g_attn_tc && pipe && !sep && al16) return launch_attn_fwd_pipe(a, p, (cudaStream_t)stream);
-  if (g_attn_tc && !sep && a->Sk <= 256 && al16)
-    return a->d_head == 32 ? launch_fwd_tc<32>(a, p, (cudaStream_t)stream) : launch_fwd_tc<64>(a, p, (cudaStream_t)stream);
+  static int pipe = -1;   // MMFM_ATTN_PIPE=0
+  if (attn_tc_enabled() && env_on("MMFM_ATTN_PIPE", &pipe) && !sep && al16)
+    return launch_attn_fwd_pipe(a, p, (cudaStream_t)stream);
   dim3 grid((a->Sq + kTile - 1) / kTile, a->n_heads, a->B);
   cudaStream_t st = (cudaStream_t)stream;
   const int nkb = (a->Sk + kTile - 1) / kTile;
@@ -2245,45 +1260,7 @@ static int launch_dkv(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t
   ATTN_DISPATCH(attn_bwd_dkv_kernel, grid, 6 * TileCfg<D>::kBytes + 4 * kTile * 4 + 2 * kTile * 4 * 2);
 }
 
-template <int D>
-static int launch_bwd_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
-  const int npk = (a->Sk + 15) / 16 * 16, npq = (a->Sq + 15) / 16 * 16;
-  const TmaSwizzle sw = (D == 32) ? TMA_SW_64 : TMA_SW_128;
-  const uint64_t width = (uint64_t)a->n_heads * D;
-  const bool drop = a->drop_p.thresh != 0u;
-  // dq: Q / dO tiles of 128 rows, K / V whole
-  CUtensorMap tq, tdo, tk, tv;
-  if (int rc = make_tmap_bf16_2d(&tq, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, 128, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tdo, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, 128, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npk, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npk, sw)) return rc;
-  const int smem = 1024 + (256 + 512) * D * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  dim3 gq((a->Sq + 127) / 128, a->n_heads, a->B);
-  if (drop) attn_bwd_dq_tc_kernel<D, true><<<gq, kTcBwdThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
-  else attn_bwd_dq_tc_kernel<D, false><<<gq, kTcBwdThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
-  MMFM_CHECK_CUDA(cudaGetLastError());
-  // dkv: K / V tiles of 128 rows, Q / dO whole
-  CUtensorMap tq2, tdo2, tk2, tv2;
-  if (int rc = make_tmap_bf16_2d(&tq2, a->q, (uint64_t)a->B * a->Sq, width, (uint64_t)a->ldq, D, npq, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tdo2, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, npq, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tk2, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, 128, sw)) return rc;
-  if (int rc = make_tmap_bf16_2d(&tv2, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, 128, sw)) return rc;
-  dim3 gk((a->Sk + 127) / 128, a->n_heads, a->B);
-  if (drop) attn_bwd_dkv_tc_kernel<D, true><<<gk, kTcBwdThreads, smem, st>>>(tq2, tdo2, tk2, tv2, p, npq);
-  else attn_bwd_dkv_tc_kernel<D, false><<<gk, kTcBwdThreads, smem, st>>>(tq2, tdo2, tk2, tv2, p, npq);
-  MMFM_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-static int launch_bwd_fused_tc(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
+static int launch_bwd_fused2(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st) {
   constexpr int D = 32;
   const int npk = (a->Sk + 15) / 16 * 16;
   const uint64_t width = (uint64_t)a->n_heads * D;
@@ -2293,38 +1270,25 @@ static int launch_bwd_fused_tc(const mmfm_attn_args* a, const AttnParams& p, cud
   if (int rc = make_tmap_bf16_2d(&tdo, a->d_o, (uint64_t)a->B * a->Sq, width, (uint64_t)a->lddo, D, 128, TMA_SW_64)) return rc;
   if (int rc = make_tmap_bf16_2d(&tk, a->k, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldk, D, npk, TMA_SW_64)) return rc;
   if (int rc = make_tmap_bf16_2d(&tv, a->v, (uint64_t)a->B * a->Sk, width, (uint64_t)a->ldv, D, npk, TMA_SW_64)) return rc;
-  const int smem = 1024 + (512 + 256) * 64 + 8 * 128 * 128;
+  const int smem = 1024 + 4 * 256 * 64 + 8 * 128 * 128;   // K, V, Q x2, dO x2 (256 rows each) + 8 slabs
   static bool attr_set = false;
   if (!attr_set) {
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   dim3 grid(a->n_heads, a->B);
-  static int piped = -1;   // MMFM_ATTN_FUSED2=0 keeps the phase-serialised fused kernel (A/B measurements)
-  if (piped < 0) {
-    const char* e = getenv("MMFM_ATTN_FUSED2");
-    piped = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (piped) {
-    const int smem2 = 1024 + 4 * 256 * 64 + 8 * 128 * 128;   // K, V, Q x2, dO x2 (256 rows each) + 8 slabs
-    static bool attr2 = false;
-    if (!attr2) {
-      MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      MMFM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      attr2 = true;
-    }
-    if (drop) attn_bwd_fused2_tc_kernel<true><<<grid, kFusedThreads, smem2, st>>>(tq, tdo, tk, tv, p, npk);
-    else attn_bwd_fused2_tc_kernel<false><<<grid, kFusedThreads, smem2, st>>>(tq, tdo, tk, tv, p, npk);
-    MMFM_CHECK_CUDA(cudaGetLastError());
-    return 0;
-  }
-  if (drop) attn_bwd_fused_tc_kernel<true><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
-  else attn_bwd_fused_tc_kernel<false><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  if (drop) attn_bwd_fused2_tc_kernel<true><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
+  else attn_bwd_fused2_tc_kernel<false><<<grid, kFusedThreads, smem, st>>>(tq, tdo, tk, tv, p, npk);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// Backward dispatch (after the prep kernel: delta = rowsum(dO * O), dO <- dO * output-dropout mask):
+//   d_head 32, Sq, Sk <= 256 (the default model)  -> persistent fused kernel (attention_bwd_persist.cu), or its
+//                                                     one-CTA-per-(batch, head) form when the side data are unaligned
+//   any other shape without modality-separation    -> streamed tcgen05 dq / dkv pair (attention_bwd_stream.cu)
+//   modality-separation mask, odd alignments        -> mma.sync dq / dkv pair
 extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   if (int rc = check_common(a, "mmfm_attention_bwd")) return rc;
   MMFM_REQUIRE(a->d_o && a->delta && a->dq && a->dk && a->dv, "mmfm_attention_bwd: null gradient buffer");
@@ -2339,51 +1303,20 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   if (a->d_head == 32) attn_bwd_prep_kernel<32><<<pgrid, 256, 0, st>>>(p);
   else attn_bwd_prep_kernel<64><<<pgrid, 256, 0, st>>>(p);
   MMFM_CHECK_CUDA(cudaGetLastError());
-  {
-    static bool env_read = false;
-    if (!env_read) {
-      const char* e = getenv("MMFM_ATTN_TC");
-      if (e && e[0] == '0') g_attn_tc = false;
-      env_read = true;
-    }
-    const int npk = (a->Sk + 15) / 16 * 16, npq = (a->Sq + 15) / 16 * 16;
-    const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
-                        reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->d_o) |
-                        reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) |
-                        reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0;
-    // TMEM budget: S and dP side by side plus the output accumulators
-    const bool fits = a->Sk <= 256 && a->Sq <= 256 && 2 * npk + a->d_head <= 512 && 2 * npq + 2 * a->d_head <= 512;
-    static int tc_bwd = -1;   // MMFM_ATTN_TC_BWD=0 falls back to the mma.sync backward pair (A/B measurements)
-    if (tc_bwd < 0) {
-      const char* e = getenv("MMFM_ATTN_TC_BWD");
-      tc_bwd = (e && e[0] == '0') ? 0 : 1;
-    }
-    static int fused = -1;    // MMFM_ATTN_FUSED_BWD=0 keeps the two-kernel tcgen05 backward
-    if (fused < 0) {
-      const char* e = getenv("MMFM_ATTN_FUSED_BWD");
-      fused = (e && e[0] == '0') ? 0 : 1;
-    }
-    static int persist = -1;   // MMFM_ATTN_PERSIST=0 keeps the one-CTA-per-(batch, head) fused kernels (A/B measurements)
-    if (persist < 0) {
-      const char* e = getenv("MMFM_ATTN_PERSIST");
-      persist = (e && e[0] == '0') ? 0 : 1;
-    }
+
+  const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+                      reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->d_o) |
+                      reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) |
+                      reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0;
+  static int tc_bwd = -1, fused = -1, persist = -1, streamed = -1;
+  const bool tc = attn_tc_enabled() && env_on("MMFM_ATTN_TC_BWD", &tc_bwd) && a->mod_q == nullptr && al16;
+  if (tc && env_on("MMFM_ATTN_FUSED_BWD", &fused) && a->d_head == 32 && a->Sq <= 256 && a->Sk <= 256) {
     const bool side_al = ((reinterpret_cast<uintptr_t>(a->lse) | reinterpret_cast<uintptr_t>(a->delta) |
                            reinterpret_cast<uintptr_t>(a->p_keep)) & 15) == 0 && a->Sq % 4 == 0;
-    if (tc_bwd && fused && persist && side_al && a->mod_q == nullptr && al16 && a->d_head == 32 && a->Sq <= 256 &&
-        a->Sk <= 256)
-      return launch_attn_bwd_persist(a, p, st);
-    if (tc_bwd && fused && a->mod_q == nullptr && al16 && a->d_head == 32 && a->Sq <= 256 && a->Sk <= 256)
-      return launch_bwd_fused_tc(a, p, st);
-    if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 32) return launch_bwd_tc<32>(a, p, st);
-    if (tc_bwd && a->mod_q == nullptr && fits && al16 && a->d_head == 64) return launch_bwd_tc<64>(a, p, st);
-    static int stream = -1;   // MMFM_ATTN_STREAM_BWD=0 keeps the mma.sync backward for long sequences
-    if (stream < 0) {
-      const char* e = getenv("MMFM_ATTN_STREAM_BWD");
-      stream = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (tc_bwd && stream && a->mod_q == nullptr && al16) return launch_attn_bwd_stream(a, p, st);
+    if (env_on("MMFM_ATTN_PERSIST", &persist) && side_al) return launch_attn_bwd_persist(a, p, st);
+    return launch_bwd_fused2(a, p, st);
   }
+  if (tc && env_on("MMFM_ATTN_STREAM_BWD", &streamed)) return launch_attn_bwd_stream(a, p, st);
   if (int rc = launch_dq(a, p, st)) return rc;
   return launch_dkv(a, p, st);
 }

@@ -81,8 +81,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
         }
       }
     }
-    return;
-  }
+  } else {
   for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
     const float* xr = x + r * H;
     bf16* yr = y + ln_out_row(r, modmajor_T, S, BT) * H;
@@ -143,6 +142,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
         *reinterpret_cast<uint2*>(yr + c) = o;
       }
     }
+  }
   }
 }
 
