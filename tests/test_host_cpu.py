@@ -134,3 +134,19 @@ def test_multi_session_model_keys_and_pickle():
     assert m.state_dict()[pre + "encoder_embeddings.ap.embedder.token_embed.weight"].shape == (80, 40)
     m2 = pickle.loads(pickle.dumps(m))
     assert m2.session_key("e1") == "s000" and m2.session_key("nope") is None
+
+
+def test_activation_arena_bump_allocation():
+    """engine.Arena: plans of different sessions alias one buffer; allocations are 256-byte aligned and bounded."""
+    import torch
+    from multi_modal_foundation_model_b200._lib import MmfmError
+    from multi_modal_foundation_model_b200.engine import Arena
+    a = Arena(4096, "cpu")
+    t1 = a.take(100)
+    t2 = a.take(300)
+    assert t1.numel() == 100 and t2.numel() == 300
+    assert (t2.data_ptr() - t1.data_ptr()) == 256 and a.off == 256 + 512
+    a.reset()
+    assert a.take(8).data_ptr() == t1.data_ptr()          # the next plan starts over on the same memory
+    with pytest.raises(MmfmError):
+        a.take(1 << 20)
