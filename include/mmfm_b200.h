@@ -211,6 +211,12 @@ int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stre
 int mmfm_u8_expand(const unsigned char* x, long long R, int C, float* y32, long long ld32, void* y16, long long ld16,
                    void* stream);
 
+/* ---- evaluation metrics (bits_per_spike / neg_log_likelihood of src/utils/eval_utils.py:
+ *      1052-1119, evaluated per neuron at :201,300,405,608,849, and r2_score per channel, :1539-1549) --------------- */
+/* pred, y: fp32 [R, C] dense.  out: 4*C doubles (zeroed here): [sum y | sum y^2 | sum (y-pred)^2 | sum (rate - y log rate)]
+ * per column, rate = exp(pred) if log_rate else pred (0 -> 1e-9). */
+int mmfm_column_stats(const float* pred, const float* y, long long R, int C, int log_rate, double* out, void* stream);
+
 /* ---- optimizer step (torch.optim.AdamW of train_multi_modal.py:197-202 over the flat
  *      master-parameter / gradient buffers; runs right after backward, trainer/base.py:196-198) ------------------- */
 /* p, g, exp_avg, exp_avg_sq: n fp32 elements each (16-byte aligned).  step >= 1 is the 1-based update count used for

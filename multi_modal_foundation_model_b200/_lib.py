@@ -147,6 +147,7 @@ SIGNATURES = {
     "mmfm_cast_bf16_multi": [_vp, _i, _i, _vp],
     "mmfm_scale_inplace": [_vp, _ll, _vp, _vp],
     "mmfm_u8_expand": [_vp, _ll, _i, _vp, _ll, _vp, _ll, _vp],
+    "mmfm_column_stats": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "mmfm_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _ll, _vp],
     "mmfm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "mmfm_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _DP, _vp, _vp, _i, _i, _i, _i, _vp],

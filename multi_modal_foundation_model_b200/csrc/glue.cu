@@ -757,6 +757,35 @@ __global__ void __launch_bounds__(256) u8_expand_kernel(const unsigned char* __r
   }
 }
 
+// Evaluation metrics: one pass over predictions p and targets y [R, C] -> four float64 sums
+// per column, [s_y | s_yy | s_err | s_nll] with s_err = sum (y - p)^2 and s_nll = sum (rate - y * log rate), rate = exp(p)
+// for log-rate predictions (zero rates become 1e-9 as in eval_utils.py:1086-1091 otherwise).  Bits per spike per neuron
+// and R^2 per channel follow from these sums (metrics.py).  CTA = a slab of rows, thread = column (strided), double
+// accumulators, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256) column_stats_kernel(const float* __restrict__ p, const float* __restrict__ y,
+                                                            long long R, int C, int log_rate, int rows_per_cta,
+                                                            double* __restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double sy = 0.0, syy = 0.0, se = 0.0, sn = 0.0;
+    for (long long r = r0; r < r1; ++r) {
+      const float yv = y[r * C + c], pv = p[r * C + c];
+      float rate, lr;
+      if (log_rate) { lr = pv; rate = expf(pv); }
+      else { rate = pv == 0.f ? 1e-9f : pv; lr = logf(rate); }
+      const float d = yv - pv;
+      sy += yv;
+      syy += (double)yv * yv;
+      se += (double)d * d;
+      sn += (double)rate - (double)yv * lr;
+    }
+    atomicAdd(out + c, sy);
+    atomicAdd(out + C + c, syy);
+    atomicAdd(out + 2ll * C + c, se);
+    atomicAdd(out + 3ll * C + c, sn);
+  }
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -963,6 +992,20 @@ extern "C" int mmfm_u8_expand(const unsigned char* x, long long R, int C, float*
                    ((uintptr_t)y16 & 7) == 0;
   if (vec) u8_expand_kernel<true><<<ew_grid(R * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, R, C, y32, ld32, (bf16*)y16, ld16);
   else u8_expand_kernel<false><<<ew_grid(R * (long long)C, 256), 256, 0, (cudaStream_t)stream>>>(x, R, C, y32, ld32, (bf16*)y16, ld16);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_column_stats(const float* pred, const float* y, long long R, int C, int log_rate, double* out,
+                                 void* stream) {
+  MMFM_REQUIRE(pred && y && out && R > 0 && C > 0, "mmfm_column_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  MMFM_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 4 * (size_t)C, st));
+  int ctas = 4 * device_sm_count();
+  int rows_per_cta = (int)((R + ctas - 1) / ctas);
+  if (rows_per_cta < 8) rows_per_cta = 8;
+  ctas = (int)((R + rows_per_cta - 1) / rows_per_cta);
+  column_stats_kernel<<<ctas, 256, 0, st>>>(pred, y, R, C, log_rate, rows_per_cta, out);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -184,6 +184,12 @@ def u8_expand(x: torch.Tensor, y32: Optional[torch.Tensor], y16: Optional[torch.
             y16.stride(0) if y16 is not None else 0, meta={"bytes": float(R) * Cc * (1 + (4 if y32 is not None else 0) + (2 if y16 is not None else 0))})
 
 
+def column_stats(pred: torch.Tensor, y: torch.Tensor, out: torch.Tensor, *, log_rate: bool) -> None:
+    R, Cc = pred.shape
+    _launch("mmfm_column_stats", pred.data_ptr(), y.data_ptr(), R, Cc, 1 if log_rate else 0, out.data_ptr(),
+            meta={"bytes": 8.0 * R * Cc})
+
+
 def adamw_step(p: torch.Tensor, g: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, *, lr: float,
                beta1: float, beta2: float, eps: float, weight_decay: float, step: int) -> None:
     n = p.numel()
