@@ -210,13 +210,6 @@ MMFM_DEVINL uint32_t my_col_bits(unsigned long long colmask, int ql) {
   return r;
 }
 
-// keep decisions of 16 random bytes: bit b = (byte b >= thresh)
-MMFM_DEVINL uint32_t keep_bits16(const uint4& w, uint32_t thresh4) {
-  const uint32_t m0 = __vcmpgeu4(w.x, thresh4) & 0x01010101u, m1 = __vcmpgeu4(w.y, thresh4) & 0x01010101u;
-  const uint32_t m2 = __vcmpgeu4(w.z, thresh4) & 0x01010101u, m3 = __vcmpgeu4(w.w, thresh4) & 0x01010101u;
-  return ((m0 * 0x01020408u) >> 24) | (((m1 * 0x01020408u) >> 24) << 4) | (((m2 * 0x01020408u) >> 24) << 8) |
-         (((m3 * 0x01020408u) >> 24) << 12);
-}
 // 16 keep bits from four byte-mask words (0xFF / 0x00 per byte)
 MMFM_DEVINL uint32_t mask_bits16(const uint32_t (&m)[4]) {
   return (((m[0] & 0x01010101u) * 0x01020408u) >> 24) | ((((m[1] & 0x01010101u) * 0x01020408u) >> 24) << 4) |

@@ -849,12 +849,19 @@ class Engine:
             im = d.get("inputs_modality")
             if not (torch.is_tensor(im) and im.is_cuda) and im is not None and int(im) != m.index:   # no D2H sync
                 raise MmfmError(f"modality {m.name}: inputs_modality {int(im)} != {m.index}")
-            if d.get("eval_mask") is None:                               # mm.py:266-267
+            em = d.get("eval_mask")
+            if em is None:                                               # mm.py:266-267
                 regions = d.get("inputs_regions") if m.name == "ap" else None
                 mk = model.masker.sample_token_mask((B, T, m.C), "cpu", regions)
                 pl.mask[m.name].copy_(mk, non_blocking=True)
-            else:                                                        # mm.py:269-270
-                pl.mask[m.name].copy_(d["eval_mask"][:, :, 0], non_blocking=True)
+            elif isinstance(em, (bool, int)):
+                # compact form: the trainer's encoding / decoding masks are all-ones or all-zeros
+                # (trainer/base.py:85-96); a scalar says so without a dense (B,T,N) int64 tensor
+                pl.mask[m.name].fill_(int(bool(em)))
+            elif em.dim() == 2:                                          # compact form: the (B,T) column the model reads
+                pl.mask[m.name].copy_(em, non_blocking=True)
+            else:                                                        # mm.py:269-270: only column 0 matters
+                pl.mask[m.name].copy_(em[:, :, 0], non_blocking=True)
         self.last_plan = pl
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.store.params.values()):
             anchor = self.store.params[self.store.bucket_order[0]]

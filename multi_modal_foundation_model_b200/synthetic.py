@@ -56,10 +56,13 @@ def make_batch(batch: int, n_neurons: int, n_behaviors: int = 2, n_bins: int = 1
 
 
 def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[str], device="cpu",
-                  extra_behaviors: int = 0) -> Dict[str, Dict[str, object]]:
+                  extra_behaviors: int = 0, compact_masks: bool = False) -> Dict[str, Dict[str, object]]:
     """Build ``mod_dict`` exactly as the trainer does (``trainer/base.py:51-103``) for multi-modal
     training: ``encoding`` (ap fully masked), ``decoding`` (behavior fully masked),
-    ``token_masking`` (eval_mask None -> Masker samples) or ``None`` (single-modality output)."""
+    ``token_masking`` (eval_mask None -> Masker samples) or ``None`` (single-modality output).
+
+    ``compact_masks`` replaces the trainer's dense (B,T,N) int64 all-ones / all-zeros ``eval_mask`` tensors (137 MB each
+    at B=256, N=668; only column 0 is ever read, mm.py:270) by the scalars 1 / 0 the B200 path also accepts."""
     spikes = batch["spikes_data"].to(device, non_blocking=True)
     target = batch["target"].to(device, non_blocking=True)
     attn = batch["time_attn_mask"].to(device, non_blocking=True)
@@ -90,10 +93,12 @@ def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[s
             d["targets"] = x.clone()
         if training_mode == "encoding":
             like = spikes
-            d["eval_mask"] = (torch.ones_like(like) if mod == "ap" else torch.zeros_like(like)).to(torch.int64)
+            d["eval_mask"] = (int(mod == "ap") if compact_masks else
+                              (torch.ones_like(like) if mod == "ap" else torch.zeros_like(like)).to(torch.int64))
         elif training_mode == "decoding":
             like = target
-            d["eval_mask"] = (torch.zeros_like(like) if mod == "ap" else torch.ones_like(like)).to(torch.int64)
+            d["eval_mask"] = (int(mod != "ap") if compact_masks else
+                              (torch.zeros_like(like) if mod == "ap" else torch.ones_like(like)).to(torch.int64))
         elif training_mode == "token_masking":
             d["eval_mask"] = None
         else:

@@ -281,3 +281,20 @@ def test_uint8_wire_format_is_exact():
     for n in res[0][1]:
         # split-R weight gradients accumulate with floating-point atomics: equal up to summation order
         assert torch.allclose(res[0][1][n], res[1][1][n], rtol=1e-4, atol=1e-7), n
+
+
+def test_compact_eval_masks_equal_dense():
+    """scalar / (B,T) eval masks give the same step as the trainer's dense (B,T,N) int64 tensors."""
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch, make_mod_dict
+    torch.manual_seed(6)
+    model = build_model(48, 2, small_config()).cuda().eval()
+    batch = make_batch(3, 48, 2, 100, step=4, pad_bins=7)
+    for mode in ("encoding", "decoding"):
+        dense = model(make_mod_dict(batch, ["ap", "behavior"], mode, device="cuda"))
+        compact = model(make_mod_dict(batch, ["ap", "behavior"], mode, device="cuda", compact_masks=True))
+        assert dense.loss.item() == compact.loss.item()
+        assert all(int(dense.mod_n_examples[m]) == int(compact.mod_n_examples[m]) for m in ("ap", "behavior"))
+    md = make_mod_dict(batch, ["ap", "behavior"], "encoding", device="cuda")
+    two_d = {m: dict(d, eval_mask=d["eval_mask"][:, :, 0].contiguous()) for m, d in md.items()}
+    assert model(two_d).loss.item() == model(md).loss.item()

@@ -9,13 +9,15 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("R,H", [(3200, 256), (1000, 1024), (77, 128), (300, 512), (50, 200)])
 def test_layernorm_fwd(R, H):
     from multi_modal_foundation_model_b200 import ops
+    torch.manual_seed(R + H)
     x = torch.randn(R, H, device="cuda") * 2 + 0.5
     g, b = torch.randn(H, device="cuda"), torch.randn(H, device="cuda")
     y = torch.empty(R, H, device="cuda", dtype=torch.bfloat16)
     mean, rstd = torch.empty(R, device="cuda"), torch.empty(R, device="cuda")
     ops.layernorm_fwd(x, g, b, y, mean, rstd, R=R, H=H)
     ref = F.layer_norm(x, (H,), g, b, 1e-5)
-    assert (y.float() - ref).abs().max().item() < 4e-2
+    # bf16 output: one rounding of the fp32 result (2^-8 relative) plus the fp32 evaluation-order difference
+    assert ((y.float() - ref).abs() <= ref.abs() * 2.0 ** -7 + 2e-3).all()
     assert (mean - x.mean(1)).abs().max().item() < 1e-5
     assert ((rstd - (x.var(1, unbiased=False) + 1e-5).rsqrt()).abs() / rstd).max().item() < 1e-4
 
