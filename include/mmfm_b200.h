@@ -207,6 +207,11 @@ int mmfm_scale_inplace(float* x, long long n, const float* scale_dev, void* stre
 /* ---- batch wire format (spike counts are small non-negative integers, stored as ubyte by
  *      the reference's datasets, dataset_utils.py:29; the dense fp32 (B,T,N) batch of loader/base.py:436-450 can be
  *      shipped as bytes) ------------------------------------------------------------------------------------------ */
+/* CSR pieces of a batch (get_binned_spikes_from_sparse, dataset_utils.py:38-43, rebuilds them with scipy on the host):
+ * data / indices of all trials concatenated, row_ptr[n_rows + 1] = global offsets of every (trial, bin) row.
+ * out: dense uint8 [n_rows, N], fully written (zero fill + scatter). */
+int mmfm_csr_to_dense_u8(const unsigned char* data, const int* indices, const long long* row_ptr, long long n_rows, int N,
+                         unsigned char* out, void* stream);
 /* x: R rows of C bytes (dense).  y32 (optional) fp32 [R, ld32]; y16 (optional) bf16 [R, ld16].  Exact conversions. */
 int mmfm_u8_expand(const unsigned char* x, long long R, int C, float* y32, long long ld32, void* y16, long long ld16,
                    void* stream);

@@ -5,5 +5,5 @@ from .masker import Masker  # noqa: F401
 from .model import (DecoderEmbedding, EncoderEmbedding, MultiModal, MultiModalOutput, MultiSessionMultiModal, build_model,  # noqa: F401
                     convert)
 from .optim import AdamW  # noqa: F401,E402
-from . import metrics  # noqa: F401,E402
+from . import metrics, sparse  # noqa: F401,E402
 from .baselines import BaselineDecoder, BaselineEncoder  # noqa: F401,E402

@@ -146,6 +146,7 @@ SIGNATURES = {
     "mmfm_cast_bf16": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _vp],
     "mmfm_cast_bf16_multi": [_vp, _i, _i, _vp],
     "mmfm_scale_inplace": [_vp, _ll, _vp, _vp],
+    "mmfm_csr_to_dense_u8": [_vp, _vp, _vp, _ll, _i, _vp, _vp],
     "mmfm_u8_expand": [_vp, _ll, _i, _vp, _ll, _vp, _ll, _vp],
     "mmfm_column_stats": [_vp, _vp, _ll, _i, _i, _vp, _vp],
     "mmfm_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _ll, _vp],

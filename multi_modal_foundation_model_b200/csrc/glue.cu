@@ -786,6 +786,34 @@ __global__ void __launch_bounds__(256) column_stats_kernel(const float* __restri
   }
 }
 
+// CSR ubyte -> dense uint8 (dataset_utils.py:38-43 rebuilds each trial with scipy on the host).
+// One warp per (trial, bin) row: the row is zero-filled with 16-byte stores where alignment allows, then its
+// non-zeros are scattered.  Column indices outside [0, N) are ignored (scipy would raise; the host checks shapes).
+__global__ void __launch_bounds__(256) csr_to_dense_u8_kernel(const unsigned char* __restrict__ data,
+                                                               const int* __restrict__ indices,
+                                                               const long long* __restrict__ row_ptr, long long n_rows,
+                                                               int N, unsigned char* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < n_rows; r += nwarps) {
+    unsigned char* row = out + r * N;
+    // zero fill: head bytes up to 16-byte alignment, 16-byte body, tail
+    const int head = (int)((16 - (reinterpret_cast<uintptr_t>(row) & 15)) & 15);
+    const int h = head < N ? head : N;
+    for (int c = lane; c < h; c += 32) row[c] = 0;
+    const int body = (N - h) >> 4;
+    for (int c = lane; c < body; c += 32) reinterpret_cast<uint4*>(row + h)[c] = make_uint4(0u, 0u, 0u, 0u);
+    for (int c = h + (body << 4) + lane; c < N; c += 32) row[c] = 0;
+    __syncwarp();
+    const long long k0 = row_ptr[r], k1 = row_ptr[r + 1];
+    for (long long k = k0 + lane; k < k1; k += 32) {
+      const int c = indices[k];
+      if (c >= 0 && c < N) row[c] = data[k];
+    }
+  }
+}
+
 }  // namespace mmfm
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1006,6 +1034,14 @@ extern "C" int mmfm_column_stats(const float* pred, const float* y, long long R,
   if (rows_per_cta < 8) rows_per_cta = 8;
   ctas = (int)((R + rows_per_cta - 1) / rows_per_cta);
   column_stats_kernel<<<ctas, 256, 0, st>>>(pred, y, R, C, log_rate, rows_per_cta, out);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_csr_to_dense_u8(const unsigned char* data, const int* indices, const long long* row_ptr,
+                                    long long n_rows, int N, unsigned char* out, void* stream) {
+  MMFM_REQUIRE(row_ptr && out && n_rows > 0 && N > 0, "mmfm_csr_to_dense_u8: bad arguments");
+  csr_to_dense_u8_kernel<<<ew_grid(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(data, indices, row_ptr, n_rows, N, out);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

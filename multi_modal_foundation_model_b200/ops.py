@@ -177,6 +177,13 @@ def scale_inplace(x: torch.Tensor, scale_dev: torch.Tensor) -> None:
     _launch("mmfm_scale_inplace", x.data_ptr(), x.numel(), scale_dev.data_ptr())
 
 
+def csr_to_dense_u8(data: torch.Tensor, indices: torch.Tensor, row_ptr: torch.Tensor, out: torch.Tensor, *,
+                    n_rows: int, n_cols: int) -> None:
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == n_rows * n_cols
+    _launch("mmfm_csr_to_dense_u8", _p(data) if data.numel() else None, _p(indices) if indices.numel() else None,
+            row_ptr.data_ptr(), n_rows, n_cols, out.data_ptr(), meta={"bytes": float(n_rows) * n_cols + 5.0 * data.numel()})
+
+
 def u8_expand(x: torch.Tensor, y32: Optional[torch.Tensor], y16: Optional[torch.Tensor], *, R: int, Cc: int) -> None:
     """uint8 [R, Cc] (dense) -> fp32 [R, *] and / or bf16 [R, *] (row pitches from the tensors)."""
     assert x.dtype == torch.uint8 and x.is_contiguous()
