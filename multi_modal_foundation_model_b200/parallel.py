@@ -67,8 +67,7 @@ class DataParallel:
         self.eng = eng
         if broadcast and self.world > 1:
             dist.broadcast(eng.store.flat, src=0, group=process_group)   # same initial weights on every rank
-        self._plans = {}
-        self._graphs = {}
+        self._graphs = []            # per-plan capture states (held here only so close() can drop the graphs)
         import atexit
         import os
         import weakref
@@ -80,17 +79,19 @@ class DataParallel:
 
     def close(self) -> None:
         """Drop the captured graphs (they hold NCCL work) -- call before ``destroy_process_group``."""
-        if not self._graphs:
+        if not any(st["graph"] is not None for st in self._graphs):
             return
         torch.cuda.synchronize()
-        self._graphs.clear()
+        for st in self._graphs:
+            st["graph"] = None
+            st["runs"] = 0
         import gc
         gc.collect()
         torch.cuda.synchronize()
 
     def _segments(self, pl):
-        key = id(pl)
-        seg = self._plans.get(key)
+        # cached on the plan object itself (an id()-keyed table could hand a new plan the entry of a freed one)
+        seg = getattr(pl, "_ddp_segments", None)
         if seg is None:
             calls = pl.bwd_calls
             # the trailing whole-buffer scale is replaced by per-bucket scaling before each all-reduce
@@ -98,7 +99,7 @@ class DataParallel:
             marks = [(min(ci, n_calls), off) for ci, off in pl.grad_marks]
             buckets = plan_buckets(marks, self.eng.store.total, self.bucket_elems)
             seg = (n_calls, buckets)
-            self._plans[key] = seg
+            pl._ddp_segments = seg
         return seg
 
     def run_backward(self, pl) -> None:
@@ -106,9 +107,10 @@ class DataParallel:
         runs eagerly (NCCL communicator set-up, kernel attributes); afterwards the whole sequence -- kernels, per-bucket
         scaling and the NCCL all-reduces on their side stream -- is captured once into a CUDA graph and replayed, so the
         multi-GPU step has the same launch-gap-free backward as the single-GPU one."""
-        st = self._graphs.get(id(pl))
+        st = getattr(pl, "_ddp_graph", None)
         if st is None:
-            st = self._graphs[id(pl)] = {"runs": 0, "graph": None}
+            st = pl._ddp_graph = {"runs": 0, "graph": None}
+            self._graphs.append(st)
         if self.eng.use_graphs and self.graph_ddp and st["graph"] is None and st["runs"] >= 1 and self.world > 1:
             try:
                 g = torch.cuda.CUDAGraph()
