@@ -51,6 +51,9 @@ def _ref(q, k, v, allowed, nh, d, keep_p=None, keep_o=None):
     (1, 8, 32, 520, 520, 1, False, 40),
     (2, 4, 64, 130, 330, 0, False, 50),       # Sq != Sk across several key blocks
     (1, 4, 64, 330, 130, 1, False, 0),
+    (2, 4, 32, 100, 100, 1, False, 10),       # one key half, one query tile (persistent fused backward, smallest form)
+    (1, 4, 32, 256, 256, 0, False, 0),        # the largest shape the fused kernels take: two full halves / tiles
+    (2, 4, 32, 200, 120, 2, False, 0),        # two query tiles over a single key half, causal
 ])
 @pytest.mark.parametrize("dropout", [False, True])
 def test_attention_fwd_bwd(B, nh, d, Sq, Sk, mode, sep, pad, dropout):
