@@ -254,14 +254,15 @@ def test_multi_session_matches_oracle_per_session():
     assert all(lo <= pl.xs[0].data_ptr() < hi for pl in eng.plans.values())   # residual streams alias one arena
 
 
-def test_uint8_wire_format_is_exact():
+@pytest.mark.parametrize("N", [72, 50])      # 50: rows that are not a multiple of 4 bytes (scalar expansion path)
+def test_uint8_wire_format_is_exact(N):
     """spike counts shipped as bytes and expanded on the device give bit-identical results to the fp32
     batch (both conversions are exact)."""
     from multi_modal_foundation_model_b200.model import build_model
     from multi_modal_foundation_model_b200.synthetic import make_batch
     torch.manual_seed(4)
-    model = build_model(72, 2, small_config()).cuda().eval()
-    batch = make_batch(3, 72, 2, 100, step=9)
+    model = build_model(N, 2, small_config()).cuda().eval()
+    batch = make_batch(3, N, 2, 100, step=9)
     g = torch.Generator().manual_seed(1)
     masks = {m: (torch.rand(3, 100, generator=g) < 0.3).long() for m in ("ap", "behavior")}
     res = []
