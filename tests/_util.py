@@ -46,3 +46,58 @@ def rel_l2(a, b):
 def cosine(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# torch restatement of oracle/philox_ref.py (so that bench-size dropout fields can be produced on the GPU in
+# seconds); checked bit for bit against the numpy original in tests/test_host_cpu.py
+# ------------------------------------------------------------------------------------------------------------
+_M0, _M1, _W0, _W1, _MASK32 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+
+
+def _philox_words_torch(g, site, c3, seed, rounds=7):
+    """g: int64 tensor of group indices -> (4, len(g)) int64 words (each < 2^32)."""
+    c0, c1 = g & _MASK32, (g >> 32) & _MASK32
+    c2 = torch.full_like(g, site & _MASK32)
+    c3 = torch.full_like(g, c3)
+    k0, k1 = seed & _MASK32, (seed >> 32) & _MASK32
+    for _ in range(rounds):
+        # products wrap modulo 2^64 in int64; the masks recover the unsigned halves
+        p0, p1 = c0 * _M0, c2 * _M1
+        hi0, lo0 = (p0 >> 32) & _MASK32, p0 & _MASK32
+        hi1, lo1 = (p1 >> 32) & _MASK32, p1 & _MASK32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + _W0) & _MASK32, (k1 + _W1) & _MASK32
+    return torch.stack([c0, c1, c2, c3])
+
+
+def _bytes_of(words):
+    """(4, G) int64 words -> (G, 16) uint8, little endian inside each word (= numpy's .view(uint8))."""
+    sh = torch.arange(4, device=words.device, dtype=torch.int64) * 8
+    return ((words.t()[:, :, None] >> sh) & 0xFF).reshape(words.shape[1], 16).to(torch.uint8)
+
+
+def philox_bytes_torch(seed, site, rows, cols, device, row0=0):
+    from oracle import philox_ref as px  # noqa: F401  (layout documented there)
+    gpr = (cols + 15) // 16
+    g = torch.arange(row0 * gpr, (row0 + rows) * gpr, device=device, dtype=torch.int64)
+    return _bytes_of(_philox_words_torch(g, site, 0, seed)).reshape(rows, gpr * 16)[:, :cols]
+
+
+def philox_keep_torch(seed, site, rows, cols, p, device, row0=0):
+    from oracle import philox_ref as px
+    by = philox_bytes_torch(seed, site, rows, cols, device, row0)
+    return (by >= px.drop_threshold(p)).float() * px.keep_scale(p)
+
+
+def philox_prob_bytes_torch(seed, site, rows, cols, device, row0=0):
+    nblk = (cols + 63) // 64
+    g = torch.arange(row0 * nblk * 4, (row0 + rows) * nblk * 4, device=device, dtype=torch.int64)
+    by = _bytes_of(_philox_words_torch(g, site, 1, seed)).reshape(rows, nblk, 4, 8, 2)     # (row, blk, q, n, e)
+    return by.permute(0, 1, 3, 2, 4).reshape(rows, nblk * 64)[:, :cols]
+
+
+def philox_prob_keep_torch(seed, site, rows, cols, p, device, row0=0):
+    from oracle import philox_ref as px
+    by = philox_prob_bytes_torch(seed, site, rows, cols, device, row0)
+    return (by >= px.drop_threshold(p)).float() * px.keep_scale(p)

@@ -1,0 +1,341 @@
+"""GPU parity AT THE BENCHMARKED SHAPE (BASELINE configs[1]: B=256 trials, T=100, N=668 -> R = 51 200 token rows).
+
+The hot kernels are persistent (grid = 148 CTAs): at this size every CTA loops over ~14 attention items / ~16-100 GEMM
+tiles, exercising the mbarrier parity wrap, the TMEM double-buffer reuse, the operand rings and the next-item
+prefetch far beyond what the small-shape tests in test_gpu_gemm.py / test_gpu_attention.py / test_gpu_model.py reach.
+Item / tile counts that are NOT multiples of the grid are included on purpose.
+
+References: fp32 torch on the same bf16-rounded operands (kernels); oracle/mm_oracle.py on the host (whole step).
+The dropout streams are checked against a torch restatement of oracle/philox_ref.py (tests/_util.py), itself
+checked against the numpy original in test_host_cpu.py.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _util import cosine, oracle_params, philox_keep_torch, philox_prob_keep_torch, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+R_BENCH = 51200      # 256 trials x 200 tokens
+
+
+def _mk(rows, cols, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ld = (cols + 7) // 8 * 8
+    return (torch.randn(rows, ld, generator=g, device="cuda") * scale).to(dtype)[:, :cols]
+
+
+def _close(out, ref, tol, what):
+    out, ref = out.float(), ref.float()
+    scale = ref.abs().max().item() + 1e-6
+    err = (out - ref).abs().max().item()
+    assert math.isfinite(err) and err <= tol * scale, f"{what}: max err {err:.4g} vs scale {scale:.4g} (tol {tol})"
+    # a persistent-loop bug typically corrupts whole tiles: also bound the mean error tightly
+    merr = (out - ref).abs().mean().item()
+    assert merr <= 0.15 * tol * scale, f"{what}: mean err {merr:.4g} vs scale {scale:.4g}"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GEMM: every epilogue flavour the step uses, M = 51 200 (400 row tiles; 800 - 4400 tiles over 148 CTAs)
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [R_BENCH, R_BENCH - 72])      # ragged last row tile as well
+def test_gemm_tn_qkv_bf16_bias(M):
+    from multi_modal_foundation_model_b200 import ops
+    N, K = 768, 256
+    A, B = _mk(M, K, seed=1), _mk(N, K, seed=2, scale=0.1)
+    bias = torch.randn(N, device="cuda")
+    D = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(A, B, D, bias=bias)
+    _close(D, A.float() @ B.float().T + bias, 8e-3, f"qkv {M}")
+
+
+@pytest.mark.parametrize("K,drop", [(256, False), (256, True), (512, True)])
+def test_gemm_tn_residual_dropout_fp32(K, drop):
+    """out-proj / down-proj flavour: fp32 out = res + dropout(A.B^T + bias)."""
+    from multi_modal_foundation_model_b200 import ops
+    M, N = R_BENCH, 256
+    A, B = _mk(M, K, seed=3), _mk(N, K, seed=4, scale=0.1)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    D = torch.zeros(M, N, device="cuda")
+    seed_val = 0x5DEECE66D1234
+    seed = torch.tensor([seed_val], dtype=torch.int64, device="cuda")
+    ops.gemm_tn(A, B, D, bias=bias, res=res, drop=ops.DropSpec(seed, 4101, 0.4) if drop else ops.NO_DROP)
+    v = A.float() @ B.float().T + bias
+    if drop:
+        v = v * philox_keep_torch(seed_val, 4101, M, N, 0.4, "cuda")
+    _close(D, v + res, 3e-3, f"res/drop K={K}")
+
+
+def test_gemm_tn_gelu_dg_and_mulaux():
+    from multi_modal_foundation_model_b200 import ops
+    from multi_modal_foundation_model_b200._lib import ACT_GELU_DG, ACT_MULAUX
+    M, N, K = R_BENCH, 512, 256
+    A, B = _mk(M, K, seed=5, scale=0.5), _mk(N, K, seed=6, scale=0.1)
+    bias = torch.randn(N, device="cuda") * 0.1
+    D = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    D2 = torch.empty_like(D)
+    ops.gemm_tn(A, B, D, bias=bias, act=ACT_GELU_DG, D2=D2)
+    v = (A.float() @ B.float().T + bias).requires_grad_(True)
+    gv = torch.nn.functional.gelu(v)
+    gv.sum().backward()
+    _close(D, gv.detach(), 8e-3, "gelu")
+    _close(D2, v.grad, 8e-3, "gelu'")
+    # backward epilogue of the down projection: du = (dY . W) * gelu'(u), K = 256 -> N = 512
+    dY, Wt = _mk(M, 256, seed=7, scale=0.1), _mk(512, 256, seed=8, scale=0.1)
+    du = torch.empty(M, 512, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(dY, Wt, du, act=ACT_MULAUX, aux=D2)
+    _close(du, (dY.float() @ Wt.float().T) * D2.float(), 8e-3, "mulaux")
+
+
+def test_gemm_tn_embedder_shapes():
+    """token_embed (softsign, N = 1336 from K = 668), projection (remap + token zeroing + residual, K = 1336),
+    its dgrad (dsoftsign), and the head (fp32, N = 668): the unaligned-pitch flavours at B*T = 25 600 rows."""
+    from multi_modal_foundation_model_b200 import ops
+    from multi_modal_foundation_model_b200._lib import ACT_DSOFTSIGN, ACT_SOFTSIGN
+    Bb, T, S, off, C, H = 256, 100, 200, 0, 668, 256
+    BT = Bb * T
+    X = _mk(BT, C, seed=9).abs().round()                               # spike-count-like
+    W1, b1 = _mk(2 * C, C, seed=10, scale=0.05), torch.randn(2 * C, device="cuda") * 0.1
+    hid = torch.empty(BT, 2 * C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(X, W1, hid, bias=b1, act=ACT_SOFTSIGN, act_scale=1.0)
+    _close(hid, torch.nn.functional.softsign(X.float() @ W1.float().T + b1), 8e-3, "token_embed")
+    W2, b2 = _mk(H, 2 * C, seed=11, scale=0.05), torch.randn(H, device="cuda") * 0.1
+    zero = torch.zeros(S, dtype=torch.uint8, device="cuda")
+    zero[off + 3], zero[off + 97] = 1, 1
+    res = torch.randn(Bb * S, H, device="cuda")
+    out = torch.zeros(Bb * S, H, device="cuda")
+    seed_val = 77
+    seed = torch.tensor([seed_val], dtype=torch.int64, device="cuda")
+    ops.gemm_tn(hid, W2, out, bias=b2, drop=ops.DropSpec(seed, 3, 0.2), remap=(T, S, off), row_zero=zero, res=res)
+    tok = (hid.float() @ W2.float().T + b2) * philox_keep_torch(seed_val, 3, BT, H, 0.2, "cuda")
+    tok = tok.view(Bb, T, H).clone()
+    tok[:, 3], tok[:, 97] = 0, 0
+    ref = torch.zeros(Bb, S, H, device="cuda")
+    ref[:, off:off + T] = tok + res.view(Bb, S, H)[:, off:off + T]
+    _close(out, ref.view(Bb * S, H), 3e-3, "projection remap/zero/res/drop")
+    assert out.view(Bb, S, H)[:, off + T:].abs().max().item() == 0.0
+    # dgrad through the softsign: dhid = (dtok . W2) * (1 - |a|)^2
+    dtok, W2t = _mk(BT, H, seed=12, scale=0.1), _mk(2 * C, H, seed=13, scale=0.05)
+    dhid = torch.empty(BT, 2 * C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tn(dtok, W2t, dhid, act=ACT_DSOFTSIGN, aux=hid, act_scale=1.0)
+    t = 1.0 - hid.float().abs()
+    _close(dhid, (dtok.float() @ W2t.float().T) * t * t, 8e-3, "dsoftsign")
+    # head
+    Y, Wo, bo = _mk(BT, H, seed=14), _mk(C, H, seed=15, scale=0.1), torch.randn(C, device="cuda")
+    pr = torch.zeros(BT, C, device="cuda")
+    ops.gemm_tn(Y, Wo, pr, bias=bo)
+    _close(pr, Y.float() @ Wo.float().T + bo, 3e-3, "head")
+
+
+@pytest.mark.parametrize("NO,KI", [(768, 256), (256, 512), (512, 256), (668, 256), (1336, 668)])
+def test_gemm_wgrad_bench_rows(NO, KI):
+    from multi_modal_foundation_model_b200 import ops
+    R = R_BENCH if NO <= 768 and KI <= 512 else R_BENCH // 2
+    dY, X = _mk(R, NO, seed=16, scale=0.1), _mk(R, KI, seed=17)
+    dW = torch.ones(NO, KI, device="cuda")
+    db = torch.full((NO,), 2.0, device="cuda")
+    ops.gemm_wgrad(dY, X, dW, dbias=db)
+    _close(dW, dY.float().T @ X.float() + 1.0, 3e-3, f"wgrad {NO}x{KI}")
+    _close(db, dY.float().sum(0) + 2.0, 3e-3, "wgrad bias")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# attention: 2048 / 264 / 256 (b, h) items over 148 persistent CTAs
+# ------------------------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, allowed, nh, d, keep_p, keep_o):
+    B, Sq, H = q.shape
+    Sk = k.shape[1]
+    qh = q.view(B, Sq, nh, d).transpose(1, 2)
+    kh = k.view(B, Sk, nh, d).transpose(1, 2)
+    vh = v.view(B, Sk, nh, d).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) / math.sqrt(d)
+    s = s.masked_fill(~allowed[:, None], float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.softmax(s, dim=-1)
+    if keep_p is not None:
+        p = p * keep_p
+    o = (p @ vh).transpose(1, 2).reshape(B, Sq, H)
+    if keep_o is not None:
+        o = o * keep_o
+    return o, lse
+
+
+@pytest.mark.parametrize("B,nh,d,S,mode,pad", [
+    (256, 8, 32, 200, 1, 0),         # the benchmarked encoder / cross-attention call: 2048 items
+    (256, 8, 32, 200, 0, 13),        # decoder self-attention with right padding
+    (33, 8, 32, 200, 1, 7),          # 264 items: not a multiple of 148
+    (16, 16, 64, 1000, 1, 50),       # the scaled config's call (streamed backward)
+    (16, 16, 64, 1000, 2, 0),        # ... causal
+])
+@pytest.mark.parametrize("dropout", [False, True])
+def test_attention_bench_shape(B, nh, d, S, mode, pad, dropout):
+    from multi_modal_foundation_model_b200 import ops
+    H = nh * d
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(B * S, 3 * H, generator=g, device="cuda").to(torch.bfloat16)
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    key_valid = torch.ones(B, S, dtype=torch.uint8, device="cuda")
+    if pad:
+        key_valid[:, S - pad:] = 0
+        key_valid[1::3, : S // 4] = 0
+    o = torch.zeros(B * S, H, device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(B, nh, S, device="cuda")
+    p_keep = torch.zeros(B * nh * S * ((S + 63) // 64) * 4, dtype=torch.int16, device="cuda")
+    seed_val = 0x0BADC0DE12345
+    seed = torch.tensor([seed_val], dtype=torch.int64, device="cuda")
+    dp = ops.DropSpec(seed, 33, 0.4) if dropout else ops.NO_DROP
+    do_ = ops.DropSpec(seed, 34, 0.4) if dropout else ops.NO_DROP
+    kw = dict(B=B, n_heads=nh, Sq=S, Sk=S, d_head=d, mask_mode=mode, drop_p=dp, drop_o=do_, p_keep=p_keep)
+    ops.attention_fwd(q, k, v, o, lse, key_valid, **kw)
+    d_o = (torch.randn(B * S, H, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    dq, dk, dv = (torch.zeros(B * S, H, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    delta = torch.zeros(B, nh, S, device="cuda")
+    ops.attention_bwd(q, k, v, o, lse, key_valid, d_o=d_o.clone(), delta=delta, dq=dq, dk=dk, dv=dv, **kw)
+    torch.cuda.synchronize()
+
+    # reference in chunks of trials (the fp32 score tensor of the whole batch would be 4 GB at S = 1000)
+    cb = 64 if S <= 256 else 4
+    if mode == 2:
+        base = torch.ones(S, S, device="cuda").tril().bool()[None]
+    for b0 in range(0, B, cb):
+        b1 = min(B, b0 + cb)
+        nb = b1 - b0
+        rows = slice(b0 * S, b1 * S)
+        if mode == 2:
+            allowed = base.expand(nb, S, S)
+        else:
+            allowed = key_valid[b0:b1].bool()[:, None, :].expand(nb, S, S)
+            if mode == 1:
+                allowed = allowed | torch.eye(S, device="cuda").bool()[None]
+        keep_p = keep_o = None
+        if dropout:
+            keep_p = philox_prob_keep_torch(seed_val, 33, nb * nh * S, S, 0.4, "cuda", row0=b0 * nh * S).view(nb, nh, S, S)
+            keep_o = philox_keep_torch(seed_val, 34, nb * S, H, 0.4, "cuda", row0=b0 * S).view(nb, S, H)
+        qf, kf, vf = (t[rows].float().reshape(nb, S, H).requires_grad_(True) for t in (q, k, v))
+        o_ref, lse_ref = _attn_ref(qf, kf, vf, allowed, nh, d, keep_p, keep_o)
+        err_o = (o[rows].float().view(nb, S, H) - o_ref).abs().max().item()
+        assert err_o < 3e-2, f"fwd trials {b0}..{b1}: max err {err_o}"
+        fin = torch.isfinite(lse_ref)
+        assert (lse[b0:b1][fin] - lse_ref[fin]).abs().max().item() < 2e-3
+        o_ref.backward(d_o[rows].float().view(nb, S, H))
+        for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+            ref = ref.reshape(nb * S, H)
+            scale = ref.abs().max().item() + 1e-6
+            err = (got[rows].float() - ref).abs().max().item()
+            assert err <= 3e-2 * scale + 1e-3, f"{name} trials {b0}..{b1}: max err {err:.4g} (scale {scale:.4g})"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# whole step vs the CPU oracle at the benchmarked batch
+# ------------------------------------------------------------------------------------------------------------
+LOSS_RTOL, PRED_ATOL, GRAD_RL2, GRAD_COS = 2e-3, 3e-2, 2e-2, 0.999
+
+
+def _step_vs_oracle(N, B, mods, dropout, mode, pad=0, n_beh=2, cfg_kw=None, grad_rl2=GRAD_RL2):
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    cfg = default_model_config(**(cfg_kw or {}))
+    torch.manual_seed(11)
+    model = build_model(N, n_beh, cfg, avail_mod=tuple(mods))
+    W = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda()
+    model.train(dropout)
+    batch = make_batch(B, N, n_beh, 100, step=2, pad_bins=pad)
+    attn, ts = batch["time_attn_mask"], batch["spikes_timestamps"]
+    g = torch.Generator().manual_seed(5)
+    xs = {"ap": batch["spikes_data"], "behavior": batch["target"]}
+    if mode == "token_masking":
+        masks = {m: (torch.rand(B, 100, generator=g) < 0.3).long() for m in mods}
+    else:
+        masks = {m: torch.full((B, 100), int((m == "ap") == (mode == "encoding")), dtype=torch.int64) for m in mods}
+    md = {}
+    for m in mods:
+        x = xs[m]
+        md[m] = dict(inputs=x.cuda(), targets=x.cuda(), inputs_attn_mask=attn.cuda(), inputs_timestamp=ts.cuda(),
+                     inputs_modality=torch.tensor(model.mod_to_indx[m], device="cuda"), masking_mode=None,
+                     eval_mask=masks[m].cuda()[:, :, None].contiguous(),
+                     inputs_regions=np.array([["CA1"] * x.shape[2]] * B))
+    # two steps on the same plan: the second one replays the CUDA graphs (the benchmarked execution mode)
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out = model({m: dict(d) for m, d in md.items()})
+        out.loss.backward()
+    torch.cuda.synchronize()
+    seed = None
+    if dropout:
+        seed = int(model.engine().last_plan.seed.item()) & 0xFFFFFFFFFFFFFFFF
+    spec = orc.OracleSpec.from_config(cfg, list(mods))
+    ob = {m: dict(inputs=xs[m], targets=xs[m], attn_mask=attn, timestamp=ts, mask=masks[m] & attn) for m in mods}
+    ref, grads = orc.forward_backward(oracle_params(W), spec, ob, dropout_seed=seed)
+    assert abs(out.loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (out.loss.item(), ref.loss.item())
+    for m in mods:
+        assert int(out.mod_n_examples[m]) == int(ref.mod_n_examples[m])
+        err = (out.mod_preds[m].detach().cpu() - ref.mod_preds[m].detach()).abs().max().item()
+        assert err < PRED_ATOL * (2 if dropout else 1), (m, err)
+    worst = (0.0, None)
+    for n, p in model.named_parameters():
+        g_ref = grads[n]
+        if g_ref.norm() < 1e-6:
+            assert p.grad is None or p.grad.float().norm().item() < 1e-4, n
+            continue
+        r, c = rel_l2(p.grad.cpu(), g_ref), cosine(p.grad.cpu(), g_ref)
+        worst = max(worst, (r, n))
+        tol = grad_rl2 * (2.0 if p.numel() < 16 else 1.0)
+        assert r < tol and c > GRAD_COS, f"{n} rel-L2 {r:.4g} cosine {c:.6f}"
+    print(f"B={B} N={N} {mode} dropout={dropout}: loss {out.loss.item():.6f} / {ref.loss.item():.6f}, worst grad {worst}")
+
+
+def test_step_b256_n668_eval_matches_oracle():
+    """The benchmarked workload itself (B = 256, N = 668), dropout off, token masking with right padding."""
+    _step_vs_oracle(668, 256, ("ap", "behavior"), False, "token_masking", pad=10)
+
+
+@pytest.mark.parametrize("mode", ["encoding", "decoding"])
+def test_step_b64_trainer_modes(mode):
+    _step_vs_oracle(668, 64, ("ap", "behavior"), False, mode)
+
+
+def test_step_b32_train_mode_matches_oracle():
+    """train(): all six dropout sites on, 256 attention items (> 148 CTAs), oracle running the same Philox stream."""
+    _step_vs_oracle(668, 32, ("ap", "behavior"), True, "token_masking", grad_rl2=3e-2)
+
+
+def test_step_spike_only_config1():
+    """BASELINE configs[0] (ii): spike-only masked transformer = MultiModal(avail_mod=['ap']) (mm.py:34-42), B = 16,
+    N = 512, token masking."""
+    _step_vs_oracle(512, 16, ("ap",), False, "token_masking")
+
+
+def test_step_b16_n512_two_modalities():
+    """trainer_mm.yaml:32 batch (16) at N = 512."""
+    _step_vs_oracle(512, 16, ("ap", "behavior"), False, "token_masking", pad=20)
+
+
+def test_baseline_encoder_n512():
+    """train_baseline.py's BaselineEncoder at the config-1 size: Linear(T*2 -> T*512) = 10.3 M parameters."""
+    from multi_modal_foundation_model_b200.baselines import BaselineEncoder
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    torch.manual_seed(0)
+    N = 512
+    m = BaselineEncoder(2, N, seq_len=100).cuda()
+    with torch.no_grad():
+        m.layer.weight.mul_(0.1)
+    b = make_batch(16, N, 2, 100)
+    x, y = b["target"].cuda(), b["spikes_data"].cuda()
+    out = m({"inputs": x, "targets": y})
+    out.loss.backward()
+    P = {"layer.weight": m.layer.weight.detach().cpu().clone().requires_grad_(True),
+         "layer.bias": m.layer.bias.detach().cpu().clone().requires_grad_(True)}
+    ref_loss, ref_preds = orc.baseline_encoder(P, x.cpu(), y.cpu())
+    gw, gb = torch.autograd.grad(ref_loss, [P["layer.weight"], P["layer.bias"]])
+    assert abs(out.loss.item() - ref_loss.item()) <= 2e-3 * abs(ref_loss.item())
+    assert (out.preds.cpu() - ref_preds).abs().max().item() < 3e-2
+    for got, ref in ((m.layer.weight.grad.cpu(), gw), (m.layer.bias.grad.cpu(), gb)):
+        assert ((got - ref).norm() / ref.norm()).item() < 2e-2

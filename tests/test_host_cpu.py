@@ -150,3 +150,16 @@ def test_activation_arena_bump_allocation():
     assert a.take(8).data_ptr() == t1.data_ptr()          # the next plan starts over on the same memory
     with pytest.raises(MmfmError):
         a.take(1 << 20)
+
+
+def test_torch_philox_restatement_matches_numpy():
+    """tests/_util.py's torch version of the dropout stream (used by the bench-size GPU tests) == oracle/philox_ref.py."""
+    from _util import philox_bytes_torch, philox_prob_bytes_torch
+    from oracle import philox_ref as px
+    for seed in (0x0BADC0DE12345FF, 0xFBADC0DE12345FF1, 7):
+        a = px.random_bytes(seed, 4101, 10, 50)
+        assert (a == philox_bytes_torch(seed, 4101, 10, 50, "cpu").numpy()).all()
+        assert (a[4:] == philox_bytes_torch(seed, 4101, 6, 50, "cpu", row0=4).numpy()).all()
+        b = px.prob_random_bytes(seed, 33, 12, 200)
+        assert (b == philox_prob_bytes_torch(seed, 33, 12, 200, "cpu").numpy()).all()
+        assert (b[7:] == philox_prob_bytes_torch(seed, 33, 5, 200, "cpu", row0=7).numpy()).all()
