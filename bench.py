@@ -49,6 +49,12 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-mode", action="store_true", help="dropout off (parity configuration)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch is the GLOBAL batch, split evenly over the ranks (SURVEY 8d config 3)")
+    ap.add_argument("--no-library-bar", action="store_true",
+                    help="skip timing the unmodified reference on the GPU through stock PyTorch")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0,
+                    help="length of the extra back-to-back leg that reports throughput under sustained clocks")
     a = ap.parse_args()
     scaled = a.workload == "scaled"
     if a.batch is None:
@@ -151,14 +157,50 @@ def workload_config(a, n_gpus):
     return {
         "workload": w.desc,
         "neurons": a.neurons, "behaviors": w.n_beh, "time_bins": w.T, "tokens_per_trial": w.S,
-        "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus,
+        "batch_per_gpu": per_gpu_batch(a, n_gpus), "global_batch": per_gpu_batch(a, n_gpus) * n_gpus,
         "mode": "eval() (dropout off)" if a.eval_mode else "train() (dropout 0.2/0.4 + masker active)",
         "training_modes": "encoding/decoding/token_masking cycled",
         "parallelism": f"dp{n_gpus}",
+        "l2_policy": "per-step working set (activations + saved tensors, several GB at B=256) >> 126 MB L2",
     }
 
 
+def per_gpu_batch(a, n_gpus):
+    if a.strong:
+        assert a.batch % n_gpus == 0, "--strong needs a global batch divisible by the number of GPUs"
+        return a.batch // n_gpus
+    return a.batch
+
+
 # ------------------------------------------------------------------------------------------------------------
+def reference_available(a) -> bool:
+    """The unmodified reference (baseline/_ref) covers the default workload; configs[3] / configs[4] (per-session
+    embedders, 5 modalities) are extensions it cannot build, so those lines fall back to the oracle port."""
+    from baseline import ref_loader
+    return a.workload == "default" and ref_loader.available()
+
+
+def cpu_reference(a, seconds: float, fixed_steps: int = 0, warmup: int = 1, threads=None, train=None):
+    """cpu_baseline dict: the reference's own CPU implementation of the path on the host cores."""
+    train = (not a.eval_mode) if train is None else train
+    if reference_available(a):
+        from baseline import ref_bench
+        w = Workload(a)
+        r = ref_bench.cpu_rate(a.neurons, w.n_beh, w.T, a.cpu_batch, steps=fixed_steps, warmup=warmup, seconds=seconds,
+                               train=train, threads=threads)
+        return {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                "sample": f"{r['steps']} fwd+bwd steps (+{r['warmup']} warm-up) of {a.cpu_batch} trials each -- a bounded "
+                          f"sample of the {a.batch}-trial workload step -- through the UNMODIFIED reference MultiModal "
+                          f"(baseline/_ref, built as train_multi_modal.py:160-189), {r['mode']}, torch fp32, "
+                          f"{r['threads']} threads of {r['cores']} cores, {r['s_per_step']:.2f} s/step",
+                "s_per_step": r["s_per_step"], "steps": r["steps"], "warmup": r["warmup"]}
+    rate, cores, n, per = cpu_reference_rate(a, seconds, fixed_steps=fixed_steps, warmup=warmup)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} fwd+bwd steps of {a.cpu_batch} trials (same model / N / T), oracle/mm_oracle.py (the reference "
+                      f"classes cannot build this extension workload), torch fp32, {cores} threads, {per:.2f} s/step",
+            "s_per_step": per, "steps": n, "warmup": warmup}
+
+
 def cpu_reference_rate(a, seconds: float, min_steps: int = 2, fixed_steps: int = 0, warmup: int = 1):
     """The reference algorithm on the host CPU: oracle/mm_oracle.py (PyTorch fp32 restatement pinned to the
     reference by tests/golden) forward + backward, all host threads.  Returns (trials/s, cores, steps, s/step)."""
@@ -226,22 +268,28 @@ def cpu_reference_rate(a, seconds: float, min_steps: int = 2, fixed_steps: int =
 
 
 def run_reference(a):
+    """--impl reference: the reference's own CPU implementation, K timed steps after W warm-up steps exactly as asked,
+    every step a bounded sample (--cpu-batch trials) of the workload step; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, a.steps)
-    # bounded: each step = one fwd+bwd over a 16-trial sample of the workload
-    rate, cores, n, per = cpu_reference_rate(a, 0.0, fixed_steps=min(steps, 12), warmup=min(max(a.warmup, 1), 2))
-    cfg = workload_config(a, a.gpus)
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    cpu = cpu_reference(a, 0.0, fixed_steps=steps, warmup=warmup)
+    extras = {}
+    if reference_available(a):
+        # BASELINE.md section 3 also asks for eval() mode and single-thread numbers (bounded: 3 / 2 steps)
+        ev = cpu_reference(a, 0.0, fixed_steps=3, warmup=1, train=False)
+        one = cpu_reference(a, 0.0, fixed_steps=2, warmup=1, threads=1)
+        extras = {"eval_mode": {"value": ev["value"], "unit": UNIT, "sample": ev["sample"]},
+                  "one_thread": {"value": one["value"], "unit": UNIT, "sample": one["sample"]}}
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": n,
-        "warmup": min(max(a.warmup, 1), 2), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} fwd+bwd steps of {a.cpu_batch} trials each (same model / N / T as the "
-                                   f"GPU arm), oracle/mm_oracle.py, torch fp32, {cores} threads"},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "strong" if a.strong else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, a.gpus),
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "extras": extras,
     }
     print(json.dumps(line))
     return 0
@@ -325,13 +373,13 @@ def main():
     torch.manual_seed(42)
     model = wl.build().to(dev)
     model.train(not a.eval_mode)
-    model.masker.stream = "fast"     # throughput mode: draw only the (B,T) field the model uses (masker.py docstring)
+    # token-masking steps use the model's DEFAULT mask stream ('device': Bernoulli field sampled inside mmfm_mask_prep)
     eng = model.engine()
     ddp = None
     if world > 1:
         from multi_modal_foundation_model_b200.parallel import DataParallel
         ddp = DataParallel(model)
-    B = a.batch
+    B = per_gpu_batch(a, world)
 
     # rank r's shard of every global batch: its own seeded trials (weak scaling: B per GPU)
     NB = len(wl.session_neurons) if wl.multi else 3    # multi-session: one batch per session, visited round-robin
@@ -400,6 +448,18 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = B * n_gpus * a.steps / (ms / 1e3)
 
+    # the same loop held for >= --sustained-seconds back to back: throughput under the clocks a long job really sees
+    sustained = None
+    if a.sustained_seconds > 0:
+        n_sus = max(a.steps, int(a.sustained_seconds / (ms / a.steps / 1e3)) + 1)
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed(step_resident, n_sus)
+        clk2 = sampler2.stop() if rank == 0 else None
+        sustained = {"value": B * n_gpus * n_sus / (ms_sus / 1e3), "unit": UNIT, "steps": n_sus,
+                     "seconds": ms_sus / 1e3, "ms_per_step": ms_sus / n_sus, "clocks": clk2}
+
     # second number of SURVEY section 8d: the same step with the optimizer (fused AdamW over the flat buffers) included
     from multi_modal_foundation_model_b200.optim import AdamW
     opt = AdamW(model.parameters(), lr=1e-4, weight_decay=0.01, eps=1e-8)
@@ -448,7 +508,7 @@ def main():
         reps = 3
         for _ in range(reps):
             pl.seed.add_(1)
-            for name, meta, t in ops.run_recorded_timed(pl.fwd_calls) + ops.run_recorded_timed(pl.bwd_calls):
+            for name, meta, t in ops.run_recorded_timed(pl.fwd_calls + pl.bwd_calls):
                 d = agg.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
                 d["ms"] += t
                 d["n"] += 1
@@ -465,10 +525,13 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = {}
+        traffic, traffic_src = {}, None
         try:   # per-launch DRAM bytes of the same command under ncu (tools/launch_summary.py), default workload only
             if a.workload == "default":
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                traffic = tj["kernels"]
+                traffic_src = ("static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu "
+                               "capture profiles/ncu_traffic.json (" + str(tj.get("captured", "round 1")) + "), not re-measured by this run")
         except Exception:
             pass
         top = next(iter(kernel_table))
@@ -485,28 +548,39 @@ def main():
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach_bw, "peak": peak_bw, "unit": "GB/s",
                         "frac": ach_bw / peak_bw, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
                         "algorithmic_bytes_per_launch": d["bytes"] / d["n"], "tensor_tflops": ach_tf,
-                        "tensor_frac": ach_tf / peak_tf, "peak_source": f"{src} hbm_gbs (copy: read + write)"}
+                        "tensor_frac": ach_tf / peak_tf, "peak_source": f"{src} hbm_gbs (copy: read + write)", "traffic_source": traffic_src}
         else:
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": ach_tf / peak_tf, "traffic": traffic.get(top, {}).get("dram_bytes_per_launch"),
                         "algorithmic_bytes_per_launch": (d["bytes"] / d["n"]) if d["bytes"] else None,
                         "hbm_gbs": ach_bw, "hbm_frac": ach_bw / peak_bw,
-                        "peak_source": f"{src} bf16_tflops_sustained"}
+                        "peak_source": f"{src} bf16_tflops_sustained", "traffic_source": traffic_src}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
-        rate, cores, n, per = cpu_reference_rate(a, a.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} fwd+bwd steps of {a.cpu_batch} trials (same model / N / T), oracle/mm_oracle.py, torch "
-                         f"fp32, {cores} threads, {per:.2f} s/step"}
+        c = cpu_reference(a, a.cpu_seconds)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    # the "library bar" (SURVEY 2.2 / 8d): the unmodified reference model on this GPU through stock PyTorch kernels
+    libbar = None
+    if rank == 0 and n_gpus == 1 and not a.no_library_bar and reference_available(a):
+        from baseline import ref_bench
+        del dev_dicts, dev_batches
+        torch.cuda.empty_cache()
+        try:
+            libbar = ref_bench.library_bar(a.neurons, wl.n_beh, wl.T, B, dev, train=not a.eval_mode)
+            for k in ("fp32_cycled", "bf16_autocast_cycled", "fp32_no_masker", "bf16_autocast_no_masker"):
+                libbar[k]["ours_over_this"] = value / libbar[k]["value"]
+        except Exception as e:                                   # the bar is a side measurement: never lose the line
+            libbar = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         cfgj = workload_config(a, n_gpus)
-        cfgj["l2_policy"] = "per-step working set (activations + saved tensors, several GB at B=256) >> 126 MB L2"
         flops_step = 3 * wl.flops_fwd_per_trial() * B
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
-            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "strong" if a.strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfgj, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
@@ -517,7 +591,11 @@ def main():
                                 "what": "e2e with spike counts shipped as uint8 and expanded on the device (8f rank 2)"}),
             "with_optimizer": {"value": value_opt, "unit": UNIT, "ms_per_step": ms_opt / a.steps,
                                "what": "fwd + bwd + fused AdamW step (mmfm_adamw_step over the flat fp32 buffers)"},
+            "sustained": sustained, "library_bar": libbar,
             "roofline": roofline, "cpu_baseline": cpu, "kernels": kernel_table,
+            "kernels_note": "per-kernel times: one CUDA event at every launch boundary of an eager pass (launch gaps "
+                            "are attributed to the following kernel; the sum is the eager step, ~5-10 % above the "
+                            "graph-replayed step that `value` times)",
             "flops_per_trial_fwd_bwd": 3 * wl.flops_fwd_per_trial(),
             "step_tensor_frac": flops_step / (ms / a.steps * 1e-3) / 1e12 / 1370.0,
         }

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMFM_ABI_VERSION 1
+#define MMFM_ABI_VERSION 2
 
 const char* mmfm_last_error(void);
 int mmfm_abi_version(void);
@@ -145,7 +145,15 @@ typedef struct mmfm_mask_args {
   const long long* mask[MMFM_MAX_MOD]; long long mask_sb[MMFM_MAX_MOD]; long long mask_st[MMFM_MAX_MOD];
   const long long* attn[MMFM_MAX_MOD]; long long attn_sb[MMFM_MAX_MOD]; long long attn_st[MMFM_MAX_MOD];
   int channels[MMFM_MAX_MOD];
+  /* Device-side token masking (the Masker's temporal mode, models/masker.py:85-86,132: an i.i.d. Bernoulli(ratio) field
+   * over (B,T)) without any host work: when sample_thresh != NULL and sample_thresh[m] (a DEVICE array of n_mod uint32,
+   * so a captured graph sees per-step changes) is non-zero, modality m's mask is drawn here instead of read from
+   * mask[m]: element e = b*T + t is masked iff word (e & 3) of Philox(counter = (e >> 2, 0, MMFM_MASK_SITE + m, 2),
+   * key = *seed) < sample_thresh[m]  (thresh = floor(ratio * 2^32); restated in oracle/philox_ref.py:mask_bernoulli). */
+  const unsigned int* sample_thresh;
+  const unsigned long long* seed;
 } mmfm_mask_args;
+#define MMFM_MASK_SITE 8192u
 /* With S = n_mod*T and mk = mask & attn (mm.py:270):
  *   zero_flags[s]   = (mk[0,s] == 1)      (mm.py:147,169 -- sample 0's mask zeroes the whole batch)
  *   key_valid[b,s]  = attn[b,s] != 0      (mm.py:152-158,178-194)

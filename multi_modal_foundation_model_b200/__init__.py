@@ -7,3 +7,4 @@ from .model import (DecoderEmbedding, EncoderEmbedding, MultiModal, MultiModalOu
 from .optim import AdamW  # noqa: F401,E402
 from . import metrics, sparse  # noqa: F401,E402
 from .baselines import BaselineDecoder, BaselineEncoder  # noqa: F401,E402
+from .dropin import install, installed, uninstall  # noqa: F401,E402

@@ -19,6 +19,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xptxas", "-v"]
 
 MAX_MOD = 8
+ABI_VERSION = 2
+MASK_SITE = 8192
 
 
 def _nvcc() -> str:
@@ -118,6 +120,7 @@ class MaskArgs(C.Structure):
         ("mask", C.c_void_p * MAX_MOD), ("mask_sb", C.c_longlong * MAX_MOD), ("mask_st", C.c_longlong * MAX_MOD),
         ("attn", C.c_void_p * MAX_MOD), ("attn_sb", C.c_longlong * MAX_MOD), ("attn_st", C.c_longlong * MAX_MOD),
         ("channels", C.c_int * MAX_MOD),
+        ("sample_thresh", C.c_void_p), ("seed", C.c_void_p),
     ]
 
 
@@ -197,7 +200,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = restype
-    if L.mmfm_abi_version() != 1:
+    if L.mmfm_abi_version() != ABI_VERSION:
         raise MmfmError("libmmfm_b200.so ABI version mismatch")
     _LIB = L
     return L

@@ -41,10 +41,20 @@ __global__ void __launch_bounds__(1024) mask_prep_kernel(const mmfm_mask_args a,
   if (threadIdx.x == 0) total = 0;
   for (int m = 0; m < a.n_mod; ++m) {
     int cnt = 0;
+    const uint32_t thresh = a.sample_thresh ? a.sample_thresh[m] : 0u;
+    const unsigned long long seed = (thresh && a.seed) ? *a.seed : 0ull;
     for (int e = threadIdx.x; e < a.B * a.T; e += blockDim.x) {
       const int b = e / a.T, t = e - b * a.T;
       const long long at = a.attn[m][(long long)b * a.attn_sb[m] + (long long)t * a.attn_st[m]];
-      long long mk = a.mask[m] ? a.mask[m][(long long)b * a.mask_sb[m] + (long long)t * a.mask_st[m]] : 0;
+      long long mk;
+      if (thresh) {   // device-side Bernoulli(ratio) field (Masker temporal mode, models/masker.py:85-86,132)
+        const uint4 w = philox4x32((uint32_t)(e >> 2), 0u, MMFM_MASK_SITE + (uint32_t)m, 2u, (uint32_t)seed,
+                                   (uint32_t)(seed >> 32));
+        const uint32_t word = (e & 3) == 0 ? w.x : (e & 3) == 1 ? w.y : (e & 3) == 2 ? w.z : w.w;
+        mk = word < thresh;
+      } else {
+        mk = a.mask[m] ? a.mask[m][(long long)b * a.mask_sb[m] + (long long)t * a.mask_st[m]] : 0;
+      }
       mk &= at;  // mm.py:270
       const long long o = (long long)b * S + m * a.T + t;
       key_valid[o] = at != 0;

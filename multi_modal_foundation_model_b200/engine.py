@@ -21,7 +21,7 @@ from typing import Any, Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import adapter, masker as _masker, ops
 from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_SOFTSIGN, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
                    MASK_KEY, MASK_KEY_OR_DIAG, CastItem, MmfmError, lib)
 from .ops import NO_DROP, DropSpec
@@ -45,6 +45,8 @@ def _pad(n: int, m: int = 8) -> int:
 class ModSpec:
     def __init__(self, name: str, index: int, channels: int, loss_kind: str):
         self.name, self.index, self.C = name, index, channels
+        if loss_kind not in ("poisson", "mse"):
+            raise NotImplementedError(f"loss kind {loss_kind!r} of modality {name!r}")
         self.loss_kind = LOSS_POISSON if loss_kind == "poisson" else LOSS_MSE
         self.small = channels <= SMALL_C
 
@@ -315,8 +317,14 @@ class Plan:
         self.attn = {m.name: i64(B, T) for m in mods}
         self.ts = {m.name: i64(B, T) for m in mods}
         self.mask = {m.name: i64(B, T) for m in mods}
-        self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.seed = eng.seed               # ONE device seed per engine: every plan's launches capture the same pointer
         self.gscale = torch.ones(1, device=dev, dtype=torch.float32)
+        # per-modality 32-bit Bernoulli thresholds of the device-side mask sampler (0 = read the mask buffer); a device
+        # array so that the captured graph sees per-step changes, staged through pinned host memory
+        self.sample_thresh = torch.zeros(len(mods), device=dev, dtype=torch.int32)
+        self._thresh_host = torch.zeros(len(mods), dtype=torch.int32).pin_memory()
+        self._thresh_cur = [0] * len(mods)
+        self._mask_host = {m.name: torch.zeros(B, T, dtype=torch.int64).pin_memory() for m in mods}
         # ---- mask products -------------------------------------------------------------------------------
         self.zero, self.kvalid, self.tmask = u8(S), u8(B, S), u8(B, S)
         self.nex, self.inv_n = i64(len(mods)), f32(1)
@@ -421,7 +429,8 @@ class Plan:
 
         sh.refresh()
         ops.mask_prep([self.mask[m.name] for m in mods], [self.attn[m.name] for m in mods], [m.C for m in mods],
-                      self.zero, self.kvalid, self.tmask, self.nex, self.inv_n)
+                      self.zero, self.kvalid, self.tmask, self.nex, self.inv_n, sample_thresh=self.sample_thresh,
+                      seed=self.seed)
 
         # ---- embeddings (encoder_embeddings.py:44-61, decoder_embeddings.py:43-61, mm.py:141-175,289,293) ----
         self.emb = {SIDE_ENC: f32(R, H), SIDE_DEC: f32(R, H)}
@@ -669,9 +678,16 @@ class Plan:
     # ---------------------------------------------------------------------------------------------------
     # -- execution: eager the first time (module load, kernel attributes), CUDA-graph replay afterwards ------
     def _fwd_body(self):
-        if self.training:
-            self.seed.add_(0x632BE59BD9B4E019)
+        # every step advances the stream (dropout sites in train(), the device-side mask sampler in either mode)
+        self.seed.add_(0x632BE59BD9B4E019)
         ops.run_recorded(self.fwd_calls)
+
+    def set_sample_thresh(self, thresh: List[int]) -> None:
+        if thresh != self._thresh_cur:
+            for k, v in enumerate(thresh):
+                self._thresh_host[k] = v - (1 << 32) if v >= (1 << 31) else v      # uint32 bit pattern in an int32
+            self.sample_thresh.copy_(self._thresh_host, non_blocking=True)
+            self._thresh_cur = list(thresh)
 
     def _bwd_body(self):
         self.eng.store.grad.zero_()
@@ -729,8 +745,13 @@ class Engine:
                             "first); there is no CPU fallback")
         lib()  # fail loudly now if the extension is missing
         self.device = p0.device
-        hp = dict(model._hp)
+        groups = embedding_groups(model)
+        hp = adapter.hyper_params(model, groups)
         self.hp = hp
+        if hp["scalenorm"]:
+            raise NotImplementedError("use_scalenorm=True (mm_utils.py:31-39) is not built in the B200 path; "
+                                      "mm.yaml:41 ships use_scalenorm: false")
+        loss_kind = adapter.loss_kinds(model)
         self.H = model.hidden_size
         self.Le, self.Ld = model.n_enc_layers, model.n_dec_layers
         self.causal, self.sep = bool(model.decoder_causal_mask), bool(model.decoder_sep_mask)
@@ -742,7 +763,6 @@ class Engine:
         self.embed_act = ACT_SOFTSIGN if act == "softsign" else ACT_NONE
         # one (prefix, modality list) per session; the reference's single-session model is the session None
         self.sessions: Dict[Any, Tuple[str, List[ModSpec]]] = {}
-        groups = embedding_groups(model)
         self.multi_session = getattr(model, "session_embeddings", None) is not None
         for prefix, enc, dec in groups:
             names = list(dec.keys())
@@ -750,10 +770,9 @@ class Engine:
                 raise NotImplementedError("encoder and decoder must embed the same modalities in the same order")
             key = prefix.split(".")[1] if self.multi_session else None
             self.sessions[key] = (prefix, [ModSpec(n, model.mod_to_indx[n], enc[n].n_channel,
-                                                   model.loss_kind.get(n, "mse")) for n in names])
+                                                   loss_kind.get(n, "mse")) for n in names])
         self.mods = next(iter(self.sessions.values()))[1]
-        e0 = groups[0][1][names[0]].embedder
-        self.embed_scale = float(e0.scale)
+        self.embed_scale = float(hp["embed_scale"])
         if self.embed_act == ACT_NONE and self.embed_scale != 1.0:
             raise NotImplementedError("identity embedder activation needs scale == 1")
         self.enc_inter = model.encoder[0].mlp.up_proj.out_features
@@ -762,6 +781,10 @@ class Engine:
             if self.H // nh not in (32, 64):
                 raise NotImplementedError(f"head size {self.H // nh}: the attention kernels are built for 32 and 64")
         self.T: Optional[int] = None
+        # the step's Philox key (dropout sites + device-side mask sampler), drawn from torch's global generator so that
+        # torch.manual_seed / the trainer's set_seed (utils/utils.py:20-29) select the stream; advanced once per step.
+        # Reseed with engine.reseed(value).
+        self.seed = torch.randint(0, 1 << 62, (1,), dtype=torch.int64).to(self.device)
         self.store = ParamStore(model, self.device)
         self.shadows = Shadows(self.store, model, self.sessions)
         self.plans: Dict[Tuple[int, bool, Any, Tuple[str, ...]], Plan] = {}
@@ -773,6 +796,8 @@ class Engine:
         self.save_gelu_grad = _os.environ.get("MMFM_GELU_SAVE", "dg") != "u"
         self.last_plan: Optional[Plan] = None
         self._grad_views = None
+        from .model import MultiModalOutput
+        self.output_cls = MultiModalOutput      # dropin.install() swaps in the reference's own dataclass
 
     # ---------------------------------------------------------------------------------------------------
     def _plan(self, B: int, T: int, training: bool, session=None, u8_mods: Tuple[str, ...] = ()) -> Plan:
@@ -799,9 +824,13 @@ class Engine:
             self.plans[key] = pl
         return pl
 
+    def reseed(self, value: int) -> None:
+        """Set the step seed (the Philox key of the dropout / mask streams); the next step uses value + one increment."""
+        self.seed.fill_(int(value) & 0x3FFFFFFFFFFFFFFF)
+
     def step(self, mod_dict: Dict[str, Dict[str, Any]]):
-        from .model import MultiModalOutput
         model = self.model
+        MultiModalOutput = self.output_cls
         if not self.store.adopted():
             self.store.adopt()
         session = None
@@ -826,7 +855,8 @@ class Engine:
             if mod_dict[m.name]["inputs"].dtype == torch.uint8 and m.name not in u8_mods:
                 raise MmfmError(f"modality {m.name}: uint8 inputs are only supported for spike-count modalities (C > {SMALL_C})")
         pl = self._plan(B, T, training, session, u8_mods)
-        for m in mods:
+        thresh = [0] * len(mods)
+        for k, m in enumerate(mods):
             d = mod_dict[m.name]
             if d["inputs"].dim() == 2:                                   # mm.py:248-250
                 d["inputs"] = d["inputs"].unsqueeze(-1)
@@ -851,9 +881,20 @@ class Engine:
                 raise MmfmError(f"modality {m.name}: inputs_modality {int(im)} != {m.index}")
             em = d.get("eval_mask")
             if em is None:                                               # mm.py:266-267
-                regions = d.get("inputs_regions") if m.name == "ap" else None
-                mk = model.masker.sample_token_mask((B, T, m.C), "cpu", regions)
-                pl.mask[m.name].copy_(mk, non_blocking=True)
+                mk = model.masker
+                stream = adapter.mask_stream(model)
+                if _masker.inactive(mk):
+                    pl.mask[m.name].zero_()
+                elif stream == "device" and _masker.device_samplable(mk):
+                    thresh[k] = max(1, min(0xFFFFFFFF, int(float(mk.ratio) * 4294967296.0)))
+                else:
+                    regions = d.get("inputs_regions") if m.name == "ap" else None          # mm.py:254
+                    col = _masker.sample_mask_column(mk, (B, T, m.C), regions,
+                                                     "fast" if stream == "device" else stream)
+                    # pinned staging: the H2D copy is asynchronous (a pageable source would make it a sync point)
+                    hb = pl._mask_host[m.name]
+                    hb.copy_(col)
+                    pl.mask[m.name].copy_(hb, non_blocking=True)
             elif isinstance(em, (bool, int)):
                 # compact form: the trainer's encoding / decoding masks are all-ones or all-zeros
                 # (trainer/base.py:85-96); a scalar says so without a dense (B,T,N) int64 tensor
@@ -862,27 +903,32 @@ class Engine:
                 pl.mask[m.name].copy_(em, non_blocking=True)
             else:                                                        # mm.py:269-270: only column 0 matters
                 pl.mask[m.name].copy_(em[:, :, 0], non_blocking=True)
+        pl.set_sample_thresh(thresh)
         self.last_plan = pl
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.store.params.values()):
-            anchor = self.store.params[self.store.bucket_order[0]]
+        anchor = None
+        if torch.is_grad_enabled():
+            anchor = next((p for p in self.store.params.values() if p.requires_grad), None)
+        if anchor is not None:
             loss = _StepFn.apply(anchor, self, pl)
-            detach = lambda t: t
         else:
             pl.run_forward()
             loss = pl.loss.clone().reshape(())
-            detach = lambda t: t.clone()
         out_loss, out_n, out_p, out_t = {}, {}, {}, {}
         mod_loss = pl.mod_loss.clone()
         nex = pl.nex.clone()
+        tmask = pl.tmask.view(B, len(mods), T).to(torch.int64)
         for k, m in enumerate(mods):
             d = mod_dict[m.name]
             out_loss[m.name] = mod_loss[k]
             out_n[m.name] = nex[k]
-            out_p[m.name] = detach(pl.preds[m.name])
+            # fresh tensors, like the reference: the plan's buffers are overwritten by the next step
+            out_p[m.name] = pl.preds[m.name].clone()
             out_t[m.name] = d["targets"]
-            # the reference leaves these keys in the caller's dict (mm.py:272-275, decoder_embeddings.py:107)
+            # the reference leaves these keys in the caller's dict (mm.py:272-275, decoder_embeddings.py:91,107)
             d["preds"] = out_p[m.name]
             d["gt"] = d["targets"]
+            d["inputs_mask"] = d["targets_mask"] = tmask[:, k]
+            d["encoder_attn_mask"] = d["decoder_attn_mask"] = d["inputs_attn_mask"]
         return MultiModalOutput(loss=loss, mod_loss=out_loss, mod_n_examples=out_n, mod_preds=out_p, mod_targets=out_t)
 
     # ---------------------------------------------------------------------------------------------------

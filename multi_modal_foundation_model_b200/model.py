@@ -260,14 +260,6 @@ class MultiModal(nn.Module):
         # mm.py:79-82; extra single-channel behaviour streams default to MSE (BASELINE config 5 extension)
         self.loss_kind = {m: ("poisson" if m == "ap" else "mse") for m in avail_mod}
 
-        self._hp = dict(
-            embed_act=cfg_get(cfg_get(enc, "embedder"), "act"),
-            embed_dropout=float(cfg_get(cfg_get(enc, "embedder"), "dropout")),
-            dec_embed_dropout=float(cfg_get(cfg_get(dec, "embedder"), "dropout")),
-            enc_heads=cfg_get(etr, "n_heads"), dec_heads=cfg_get(dtr, "n_heads"),
-            enc_dropout=float(cfg_get(etr, "dropout")), dec_dropout=float(cfg_get(dtr, "dropout")),
-            enc_act=cfg_get(etr, "act"), dec_act=cfg_get(dtr, "act"),
-        )
         self._engine = None
 
     def share_modality_embeddings(self):

@@ -90,20 +90,19 @@ def count_kernels(calls) -> int:
 
 
 def run_recorded_timed(calls):
-    """One pass with a CUDA-event pair around every call; returns [(name, meta, ms)] (profiling aid for bench.py:
-    events on the launching stream, never used for the headline number)."""
+    """One eager pass with ONE CUDA event at every launch boundary; returns [(name, meta, ms)] where ms spans from the
+    boundary before the call to the boundary after it (so the times sum to the pass; profiling aid for bench.py: events
+    on the launching stream, never used for the headline number)."""
     st = _stream()
-    evs = []
-    for c in calls:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
+    evs[0].record()
+    for i, c in enumerate(calls):
         rc = c[0](*c[1], st)
-        e1.record()
+        evs[i + 1].record()
         if rc != 0:
             check(rc, c[2])
-        evs.append((c[2], c[3], e0, e1))
     torch.cuda.synchronize()
-    return [(n, m, e0.elapsed_time(e1)) for n, m, e0, e1 in evs]
+    return [(c[2], c[3], evs[i].elapsed_time(evs[i + 1])) for i, c in enumerate(calls)]
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -262,9 +261,14 @@ def attention_bwd(q, k, v, o, lse, key_valid, **kw) -> None:
 
 
 def mask_prep(masks: Sequence[Optional[torch.Tensor]], attns: Sequence[torch.Tensor], channels: Sequence[int],
-              zero_flags, key_valid, tok_mask, n_examples, inv_n) -> None:
-    """masks[m]: (B,T) int64 view (any strides) or None; attns[m]: (B,T) int64 view."""
+              zero_flags, key_valid, tok_mask, n_examples, inv_n, sample_thresh: Optional[torch.Tensor] = None,
+              seed: Optional[torch.Tensor] = None) -> None:
+    """masks[m]: (B,T) int64 view (any strides) or None; attns[m]: (B,T) int64 view.  sample_thresh: optional device
+    int32/uint32 [n_mod]; a non-zero entry makes the kernel draw that modality's Bernoulli mask itself (see the header)."""
     a = MaskArgs()
+    if sample_thresh is not None:
+        assert sample_thresh.element_size() == 4 and sample_thresh.numel() >= len(attns) and seed is not None
+    a.sample_thresh, a.seed = _p(sample_thresh), _p(seed)
     a.n_mod = len(attns)
     a.B, a.T = attns[0].shape
     for m, (mk, at) in enumerate(zip(masks, attns)):

@@ -122,3 +122,29 @@ SIDE_DEC = 1
 
 def site_id(kind: int, layer: int, side: int) -> int:
     return kind + 16 * layer + 4096 * side
+
+
+# ---------------------------------------------------------------------------------------------
+# Device-side token masking (the Masker's temporal mode sampled by mmfm_mask_prep, see include/mmfm_b200.h)
+# ---------------------------------------------------------------------------------------------
+MASK_SITE = 8192
+
+
+def mask_threshold(ratio: float) -> int:
+    """32-bit threshold: element masked iff its random word < floor(ratio * 2^32)."""
+    return max(0, min(0xFFFFFFFF, int(float(ratio) * 4294967296.0)))
+
+
+def mask_bernoulli(seed: int, mod_index: int, B: int, T: int, ratio: float) -> np.ndarray:
+    """(B,T) int64 Bernoulli(ratio) field of modality ``mod_index``: element e = b*T + t reads word (e & 3) of
+    Philox(counter = (e >> 2, 0, MASK_SITE + mod_index, 2), key = seed).  Stands in for the i.i.d. field of
+    models/masker.py:85-86,132 (distribution-identical; the reference draws it from the CPU mt19937 stream)."""
+    n = B * T
+    g = np.arange((n + 3) // 4, dtype=np.uint64)
+    c0 = (g & _MASK32).astype(np.uint32)
+    c1 = np.zeros_like(c0)
+    c2 = np.full_like(c0, np.uint32(MASK_SITE + mod_index))
+    c3 = np.full_like(c0, np.uint32(2))
+    w = philox4x32(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=1).reshape(-1)[:n]
+    return (words < np.uint32(mask_threshold(ratio))).astype(np.int64).reshape(B, T)

@@ -172,6 +172,7 @@ def test_masker_path_and_grad_accumulation():
     from multi_modal_foundation_model_b200.synthetic import make_batch, make_mod_dict
     torch.manual_seed(0)
     model = build_model(48, 2, small_config()).cuda().eval()
+    model.masker.stream = "reference"          # host stream replay (the default samples on the device)
     batch = make_batch(4, 48, 2, 100, step=3)
     torch.manual_seed(77)
     md = make_mod_dict(batch, ["ap", "behavior"], "token_masking", device="cuda")

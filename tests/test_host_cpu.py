@@ -24,7 +24,7 @@ def test_masker_bit_exact_against_reference_masks():
     for i in range(n):
         seed, B, T, C, r1000 = [int(v) for v in z[f"case{i}/meta"]]
         cfg = default_model_config(mask_ratio=r1000 / 1000.0)
-        mk = Masker(cfg["masker"])
+        mk = Masker(cfg["masker"], stream="reference")
         torch.manual_seed(seed)
         regions = np.array([["CA1"] * C] * B)
         for call in range(3):
@@ -45,10 +45,10 @@ def test_masker_early_outs_and_forward_shape():
     mk.force_active = False
     mk.eval()
     assert mk.sample_token_mask((2, 10, 3), "cpu").sum() == 0
-    mk.mode = "neuron"
+    mk.mode = "no-such-mode"
     mk.train()
-    with pytest.raises(NotImplementedError):
-        mk.sample_token_mask((2, 10, 3), "cpu")
+    with pytest.raises(Exception):                      # masker.py:129
+        mk.sample_token_mask((2, 10, 3), "cpu", np.array([["CA1"] * 3] * 2))
 
 
 def test_initial_weights_match_reference_seed42():
@@ -97,7 +97,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().mmfm_abi_version() == 1
+    assert _lib.lib().mmfm_abi_version() == _lib.ABI_VERSION
     # no compute call without a GPU: bad arguments are rejected on the host with a message
     assert _lib.lib().mmfm_gemm_tn(None, None) == -1
     assert b"null args" in _lib.lib().mmfm_last_error()
@@ -163,3 +163,28 @@ def test_torch_philox_restatement_matches_numpy():
         b = px.prob_random_bytes(seed, 33, 12, 200)
         assert (b == philox_prob_bytes_torch(seed, 33, 12, 200, "cpu").numpy()).all()
         assert (b[7:] == philox_prob_bytes_torch(seed, 33, 5, 200, "cpu", row0=7).numpy()).all()
+
+
+def test_masker_every_mode_bit_exact_vs_reference_golden():
+    """the column-0 mask of EVERY reference masking mode (models/masker.py:79-168), three consecutive
+    calls each, equals the unmodified reference's (tests/golden/make_masker_modes.py) -- torch CPU stream and python
+    `random` consumption included."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_masker_modes as gm
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.masker import Masker
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "masker_modes.npz"))
+    for i, (mode, seed, shape, over) in enumerate(gm.CASES):
+        cfg = default_model_config()["masker"]
+        cfg["mode"] = mode
+        cfg.update(over)
+        mk = Masker(cfg, stream="reference")
+        torch.manual_seed(seed)
+        random.seed(seed)
+        regions = gm.regions_for(shape[0], shape[2])
+        for call in range(3):
+            got = mk.sample_token_mask(shape, "cpu", regions).numpy()
+            assert (got == z[f"case{i}"][call]).all(), (mode, i, call)
