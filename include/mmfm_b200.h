@@ -103,6 +103,13 @@ int mmfm_layernorm_bwd(const void* dy, const float* x, const float* mean, const 
                        const float* dres, float* dx, void* dxb, const mmfm_dropout* drop, float* dgamma,
                        float* dbeta, int R, int H, int modmajor_T, int S, void* stream);
 
+/* ---- ScaleNorm (mm_utils.py:31-39, config `use_scalenorm: true`): y(bf16) = x * g[0] / max(||x||_2, eps); the
+ *      reciprocal norms are saved in rnorm[R].  Backward: dx = dres + g*rnorm*(dy - xhat <dy,xhat>), optional
+ *      dropout-masked bf16 copy dxb (as in mmfm_layernorm_bwd), dg[0] += sum_rows <dy, xhat>. ------------------- */
+int mmfm_scalenorm_fwd(const float* x, const float* g, void* y, float* rnorm, int R, int H, float eps, void* stream);
+int mmfm_scalenorm_bwd(const void* dy, const float* x, const float* rnorm, const float* g, const float* dres, float* dx,
+                       void* dxb, const mmfm_dropout* drop, float* dg, int R, int H, float eps, void* stream);
+
 /* ---- masked attention (flash-style; F.scaled_dot_product_attention with the (B,S,S) bool masks of
  *      mm.py:152-158,178-194 evaluated as predicates; mm_utils.py:105-112,143-150) ------------------------ */
 enum mmfm_mask_mode {
@@ -187,7 +194,12 @@ int mmfm_smallc_head_bwd(const void* y, const float* W, const void* dpreds, long
                          float* db, int R, int H, int C, void* stream);
 
 /* ---- fused masked loss + gradient (mm.py:217-239; nn.PoissonNLLLoss(log_input=True) :80, nn.MSELoss :81) -- */
-enum mmfm_loss_kind { MMFM_LOSS_POISSON = 0, MMFM_LOSS_MSE = 1 };
+enum mmfm_loss_kind {
+  MMFM_LOSS_POISSON = 0, MMFM_LOSS_MSE = 1,
+  /* categorical stream (choice / block -- an extension, the reference has none): targets = one-hot / class
+   * probabilities over the C classes; ell[.,k] = -t_k * log_softmax(preds)_k, C <= 64 */
+  MMFM_LOSS_CE = 2
+};
 /* preds, targets fp32 [B*T, C] contiguous; tok_mask [B,S] bytes, this modality at columns off..off+T-1.
  * partials[i] = CTA i's share of sum(mask * ell(preds, targets)) (n_partials CTAs, fixed-order finalize);
  * dpreds (bf16, pitch lddp) = mask * ell' * inv_n[0]. */

@@ -136,7 +136,7 @@ class CastItem(C.Structure):
 
 ACT_NONE, ACT_GELU, ACT_SOFTSIGN, ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU_DG, ACT_MULAUX = 0, 1, 2, 3, 4, 5, 6
 MASK_KEY, MASK_KEY_OR_DIAG, MASK_CAUSAL = 0, 1, 2
-LOSS_POISSON, LOSS_MSE = 0, 1
+LOSS_POISSON, LOSS_MSE, LOSS_CE = 0, 1, 2
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _DP = C.POINTER(Dropout)
@@ -155,6 +155,8 @@ SIGNATURES = {
     "mmfm_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _ll, _vp],
     "mmfm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "mmfm_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _DP, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mmfm_scalenorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "mmfm_scalenorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _DP, _vp, _i, _i, _f, _vp],
     "mmfm_attention_fwd": [C.POINTER(AttnArgs), _vp],
     "mmfm_attention_bwd": [C.POINTER(AttnArgs), _vp],
     "mmfm_mask_prep": [C.POINTER(MaskArgs), _vp, _vp, _vp, _vp, _vp, _vp],

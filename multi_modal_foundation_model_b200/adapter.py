@@ -81,8 +81,8 @@ def hyper_params(model, enc_groups) -> Dict[str, object]:
 
 def loss_kinds(model) -> Dict[str, str]:
     """modality -> 'poisson' | 'mse' | 'ce'.  Our classes keep ``loss_kind``; the reference keeps loss modules
-    (``loss_mod``, mm.py:79-82: PoissonNLLLoss(log_input=True) / MSELoss; CrossEntropyLoss for a categorical stream --
-    an extension, the reference has none)."""
+    (``loss_mod``, mm.py:79-82: PoissonNLLLoss(log_input=True) / MSELoss; losses.TokenCrossEntropy for a categorical
+    stream -- an extension, the reference has none)."""
     lk = getattr(model, "loss_kind", None)
     if lk is not None:
         return dict(lk)
@@ -94,8 +94,8 @@ def loss_kinds(model) -> Dict[str, str]:
             out[m] = "poisson"
         elif isinstance(fn, nn.MSELoss):
             out[m] = "mse"
-        elif isinstance(fn, nn.CrossEntropyLoss):
-            out[m] = "ce"
+        elif getattr(fn, "b200_kind", None) in LOSS_KINDS:          # losses.TokenCrossEntropy
+            out[m] = fn.b200_kind
         else:
             raise NotImplementedError(f"loss {type(fn).__name__} of modality {m!r} is not built")
     return out

@@ -42,9 +42,9 @@ def _embedder(n_modality: int, max_F: int) -> Dict[str, Any]:
                 act="softsign", scale=1, bias=True, dropout=0.2)
 
 
-def _transformer(n_layers: int, hidden_size: int, n_heads: int, inter_size: int) -> Dict[str, Any]:
+def _transformer(n_layers: int, hidden_size: int, n_heads: int, inter_size: int, use_scalenorm: bool = False) -> Dict[str, Any]:
     # mm.yaml:38-48 / 68-78
-    return dict(n_layers=n_layers, hidden_size=hidden_size, use_scalenorm=False, n_heads=n_heads,
+    return dict(n_layers=n_layers, hidden_size=hidden_size, use_scalenorm=use_scalenorm, n_heads=n_heads,
                 attention_bias=True, act="gelu", inter_size=inter_size, mlp_bias=True, dropout=0.4,
                 fixup_init=True)
 
@@ -59,6 +59,7 @@ def default_model_config(
     mask_ratio: float = 0.3,
     decoder_sep_mask: bool = False,
     decoder_causal_mask: bool = False,
+    use_scalenorm: bool = False,
     overrides: Optional[Mapping[str, Any]] = None,
 ) -> DotDict:
     """Hyper-parameters of the reference's ``mm.yaml`` (defaults) as a dot-access dict.
@@ -77,14 +78,14 @@ def default_model_config(
         encoder=dict(
             from_pt=None,
             embedder=_embedder(n_modality, max_F),
-            transformer=_transformer(n_layers, hidden_size, n_heads, inter_size),
+            transformer=_transformer(n_layers, hidden_size, n_heads, inter_size, use_scalenorm),
         ),
         decoder=dict(
             from_pt=None,
             decoder_sep_mask=decoder_sep_mask,  # mm.yaml:54-55
             decoder_causal_mask=decoder_causal_mask,
             embedder=_embedder(n_modality, max_F),
-            transformer=_transformer(n_layers, hidden_size, n_heads, inter_size),
+            transformer=_transformer(n_layers, hidden_size, n_heads, inter_size, use_scalenorm),
         ),
     )
     if overrides:

@@ -646,6 +646,50 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ pre
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// Masked categorical cross-entropy over the class axis (the choice / block streams; BASELINE.json north_star -- an
+// extension: the reference has no categorical modality).  The loss module slots into the
+// reference's forward_loss unchanged (mm.py:229-231): ell[b,t,k] = -targets[b,t,k] * log_softmax(preds[b,t,:])[k],
+// summed under the (B,T)->(B,T,K) expanded mask and normalised by the expanded mask count like every other modality.
+// thread = one token row (K <= kMaxClasses classes in registers); grad = mask * inv_n * (softmax * sum_k t_k - t).
+constexpr int kMaxClasses = 64;
+__global__ void __launch_bounds__(256) loss_ce_kernel(const float* __restrict__ preds, const float* __restrict__ targets,
+                                                       const unsigned char* __restrict__ tok_mask, int S, int off,
+                                                       const float* __restrict__ inv_n, int B, int T, int C,
+                                                       float* __restrict__ partials, bf16* __restrict__ dpreds,
+                                                       long long lddp) {
+  __shared__ float sh[32];
+  const float invn = __ldg(inv_n);
+  float acc = 0.f;
+  const long long rows = (long long)B * T;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long b = r / T;
+    const int t = (int)(r - b * T);
+    const bool mk = tok_mask[b * S + off + t] != 0;
+    const float* pr = preds + r * C;
+    const float* tg = targets + r * C;
+    bf16* dp = dpreds + r * lddp;
+    if (!mk) {
+      for (int c = 0; c < C; ++c) dp[c] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    float mx = -INFINITY, tsum = 0.f;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, pr[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += __expf(pr[c] - mx);
+    const float lse = mx + __logf(se);
+    for (int c = 0; c < C; ++c) {
+      const float tc = tg[c];
+      tsum += tc;
+      acc -= tc * (pr[c] - lse);
+    }
+    const float inv_se = 1.0f / se;
+    for (int c = 0; c < C; ++c)
+      dp[c] = __float2bfloat16_rn((__expf(pr[c] - mx) * inv_se * tsum - tg[c]) * invn);
+  }
+  const float s = block_sum(acc, sh);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int n_partials, int n_mod,
                                                              const float* __restrict__ inv_n, float* __restrict__ mod_loss,
                                                              float* __restrict__ loss) {
@@ -973,13 +1017,16 @@ extern "C" int mmfm_loss_fwd_bwd(const float* preds, const float* targets, const
                                  const float* inv_n, int kind, int B, int T, int C, float* partials, int n_partials,
                                  void* dpreds, long long lddp, void* stream) {
   MMFM_REQUIRE(preds && targets && tok_mask && inv_n && partials && dpreds, "mmfm_loss_fwd_bwd: null pointer");
-  MMFM_REQUIRE(kind == MMFM_LOSS_POISSON || kind == MMFM_LOSS_MSE, "mmfm_loss_fwd_bwd: bad loss kind %d", kind);
+  MMFM_REQUIRE(kind == MMFM_LOSS_POISSON || kind == MMFM_LOSS_MSE || kind == MMFM_LOSS_CE, "mmfm_loss_fwd_bwd: bad loss kind %d", kind);
   MMFM_REQUIRE(B > 0 && T > 0 && C > 0 && n_partials > 0 && lddp >= C, "mmfm_loss_fwd_bwd: bad shape");
   const bool vec = (C % 4 == 0) && (lddp % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   bf16* dp = (bf16*)dpreds;
 #define LOSS(K, V) loss_kernel<K, V><<<n_partials, 256, 0, st>>>(preds, targets, tok_mask, S, off, inv_n, B, T, C, partials, dp, lddp)
-  if (kind == MMFM_LOSS_POISSON) { if (vec) LOSS(MMFM_LOSS_POISSON, true); else LOSS(MMFM_LOSS_POISSON, false); }
+  if (kind == MMFM_LOSS_CE) {
+    MMFM_REQUIRE(C <= kMaxClasses, "mmfm_loss_fwd_bwd: cross-entropy supports up to %d classes (got %d)", kMaxClasses, C);
+    loss_ce_kernel<<<n_partials, 256, 0, st>>>(preds, targets, tok_mask, S, off, inv_n, B, T, C, partials, dp, lddp);
+  } else if (kind == MMFM_LOSS_POISSON) { if (vec) LOSS(MMFM_LOSS_POISSON, true); else LOSS(MMFM_LOSS_POISSON, false); }
   else { if (vec) LOSS(MMFM_LOSS_MSE, true); else LOSS(MMFM_LOSS_MSE, false); }
 #undef LOSS
   MMFM_CHECK_CUDA(cudaGetLastError());

@@ -242,6 +242,107 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// ScaleNorm (mm_utils.py:31-39, `use_scalenorm: true`): y = x * g / max(||x||_2, eps), g a scalar parameter.
+// Warp per row, any H % 4 == 0 (the row is re-read through L1 for the second pass).  Off the default config's path
+// (mm.yaml:41 ships use_scalenorm: false), so these are plain bandwidth kernels without the register-path variants.
+// rnorm[r] = 1 / max(||x_r||, eps) is saved for the backward.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLnWarps * 32) scalenorm_fwd_kernel(const float* __restrict__ x,
+                                                                       const float* __restrict__ g,
+                                                                       bf16* __restrict__ y, float* __restrict__ rnorm,
+                                                                       int R, int H, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = __ldg(g);
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
+    const float* xr = x + r * H;
+    float q = 0.f;
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      q += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
+    }
+    const float rn = 1.0f / fmaxf(sqrtf(warp_sum(q)), eps);
+    if (lane == 0) rnorm[r] = rn;
+    const float k = gs * rn;
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      uint2 o;
+      o.x = pack_bf16x2(t.x * k, t.y * k);
+      o.y = pack_bf16x2(t.z * k, t.w * k);
+      *reinterpret_cast<uint2*>(y + r * H + c) = o;
+    }
+  }
+}
+
+// dx = dres + g * rn * (dy - xhat * <dy, xhat>), xhat = x * rn  (the projection term vanishes where the norm was clamped
+// to eps: there the scale g / eps is a constant);  dg += sum_rows <dy, xhat>
+__global__ void __launch_bounds__(kLnWarps * 32) scalenorm_bwd_kernel(const bf16* __restrict__ dy,
+                                                                       const float* __restrict__ x,
+                                                                       const float* __restrict__ rnorm,
+                                                                       const float* __restrict__ g, const float* dres,
+                                                                       float* dx, bf16* __restrict__ dxb, DropCfg drop,
+                                                                       float* __restrict__ dg, int R, int H, float eps) {
+  __shared__ float red[kLnWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = __ldg(g);
+  unsigned long long seed = 0ull;
+  if (drop.thresh != 0u) seed = *drop.seed;
+  const uint32_t gpr = (uint32_t)((H + 15) >> 4);
+  float acc_g = 0.f;
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
+    const float* xr = x + r * H;
+    const bf16* dyr = dy + r * H;
+    const float rn = __ldg(rnorm + r);
+    float s = 0.f;
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      const uint2 dv = __ldg(reinterpret_cast<const uint2*>(dyr + c));
+      const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+      s += (d01.x * t.x + d01.y * t.y) + (d23.x * t.z + d23.y * t.w);
+    }
+    const float dot = warp_sum(s) * rn;            // <dy, xhat>
+    acc_g += dot;
+    const bool clamped = rn >= 1.0f / eps;         // ||x|| <= eps
+    const float proj = clamped ? 0.f : dot * rn;   // xhat * <dy, xhat> = x * (rn * dot)
+    const float k = gs * rn;
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xr + c));
+      const uint2 dv = __ldg(reinterpret_cast<const uint2*>(dyr + c));
+      const float2 d01 = unpack_bf16x2(dv.x), d23 = unpack_bf16x2(dv.y);
+      float4 o;
+      o.x = k * (d01.x - t.x * proj); o.y = k * (d01.y - t.y * proj);
+      o.z = k * (d23.x - t.z * proj); o.w = k * (d23.y - t.w * proj);
+      if (dres) {
+        const float4 dr = *reinterpret_cast<const float4*>(dres + r * H + c);
+        o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
+      }
+      if (dx) *reinterpret_cast<float4*>(dx + r * H + c) = o;
+      if (dxb) {
+        if (drop.thresh != 0u) {
+          const uint4 w = drop_bytes16(seed, drop.site, (uint64_t)r, gpr, (uint32_t)(c >> 4));
+          const int b0 = c & 15;
+          o.x = (drop_byte(w, b0) < drop.thresh) ? 0.f : o.x * drop.scale;
+          o.y = (drop_byte(w, b0 + 1) < drop.thresh) ? 0.f : o.y * drop.scale;
+          o.z = (drop_byte(w, b0 + 2) < drop.thresh) ? 0.f : o.z * drop.scale;
+          o.w = (drop_byte(w, b0 + 3) < drop.thresh) ? 0.f : o.w * drop.scale;
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dxb + r * H + c) = pk;
+      }
+    }
+  }
+  if (lane == 0) red[warp] = acc_g;
+  __syncthreads();
+  if (threadIdx.x == 0 && dg) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) t += red[w];
+    atomicAdd(dg, t);
+  }
+}
+
 }  // namespace mmfm
 
 using namespace mmfm;
@@ -319,6 +420,37 @@ extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* m
     default: LN_BWD(8); break;
   }
 #undef LN_BWD
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_scalenorm_fwd(const float* x, const float* g, void* y, float* rnorm, int R, int H, float eps,
+                                  void* stream) {
+  MMFM_REQUIRE(x && g && y && rnorm, "mmfm_scalenorm_fwd: null pointer");
+  MMFM_REQUIRE(R > 0 && H > 0 && H % 4 == 0, "mmfm_scalenorm_fwd: bad shape R=%d H=%d (H must be a multiple of 4)", R, H);
+  scalenorm_fwd_kernel<<<ln_grid(R), kLnWarps * 32, 0, (cudaStream_t)stream>>>(x, g, (bf16*)y, rnorm, R, H, eps);
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_scalenorm_bwd(const void* dy, const float* x, const float* rnorm, const float* g, const float* dres,
+                                  float* dx, void* dxb, const mmfm_dropout* drop, float* dg, int R, int H, float eps,
+                                  void* stream) {
+  MMFM_REQUIRE(dy && x && rnorm && g, "mmfm_scalenorm_bwd: null pointer");
+  MMFM_REQUIRE(dx || dxb, "mmfm_scalenorm_bwd: no output requested");
+  MMFM_REQUIRE(R > 0 && H > 0 && H % 4 == 0, "mmfm_scalenorm_bwd: bad shape R=%d H=%d", R, H);
+  DropCfg dc{nullptr, 0u, 0u, 1.0f};
+  if (drop && drop->thresh != 0u) {
+    MMFM_REQUIRE(drop->seed != nullptr && drop->thresh < 256u, "mmfm_scalenorm_bwd: bad dropout config");
+    dc = DropCfg{drop->seed, drop->site, drop->thresh, drop->scale};
+  }
+  static int cap = 0;
+  if (cap == 0) cap = resident_ctas(scalenorm_bwd_kernel, kLnWarps * 32);
+  int grid = (R + kLnWarps * 4 - 1) / (kLnWarps * 4);
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  scalenorm_bwd_kernel<<<grid, kLnWarps * 32, 0, (cudaStream_t)stream>>>((const bf16*)dy, x, rnorm, g, dres, dx, (bf16*)dxb,
+                                                                        dc, dg, R, H, eps);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import adapter, masker as _masker, ops
-from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_SOFTSIGN, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
+from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_SOFTSIGN, LOSS_CE, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
                    MASK_KEY, MASK_KEY_OR_DIAG, CastItem, MmfmError, lib)
 from .ops import NO_DROP, DropSpec
 
@@ -45,9 +45,9 @@ def _pad(n: int, m: int = 8) -> int:
 class ModSpec:
     def __init__(self, name: str, index: int, channels: int, loss_kind: str):
         self.name, self.index, self.C = name, index, channels
-        if loss_kind not in ("poisson", "mse"):
+        if loss_kind not in ("poisson", "mse", "ce"):
             raise NotImplementedError(f"loss kind {loss_kind!r} of modality {name!r}")
-        self.loss_kind = LOSS_POISSON if loss_kind == "poisson" else LOSS_MSE
+        self.loss_kind = {"poisson": LOSS_POISSON, "mse": LOSS_MSE, "ce": LOSS_CE}[loss_kind]
         self.small = channels <= SMALL_C
 
 
@@ -105,7 +105,8 @@ class ParamStore:
     @staticmethod
     def _execution_reverse_order(model, named) -> List[str]:
         def lin(prefix):
-            return [f"{prefix}.weight", f"{prefix}.bias"]
+            # Linear / LayerNorm: weight + bias; ScaleNorm (use_scalenorm, mm_utils.py:31-39): one scalar `scale`
+            return [f"{prefix}.weight", f"{prefix}.bias", f"{prefix}.scale"]
 
         def attn(prefix, fused_q: bool):
             o = lin(f"{prefix}.out_proj")
@@ -360,12 +361,20 @@ class Plan:
         mean, rstd = torch.empty(self.R, device=x.device), torch.empty(self.R, device=x.device)
         self._keep += [mean, rstd]
         stats[name] = (mean, rstd)
+        if st.has(name + ".scale"):       # ScaleNorm: `mean` unused, `rstd` holds 1 / max(||x||, eps)
+            assert not modmajor
+            ops.scalenorm_fwd(x, st.p(name + ".scale"), y, rstd, R=self.R, H=self.eng.H)
+            return
         ops.layernorm_fwd(x, st.p(name + ".weight"), st.p(name + ".bias"), y, mean, rstd, R=self.R, H=self.eng.H,
                           modmajor_T=self.eng.T if modmajor else 0, S=self.S if modmajor else 0)
 
     def _ln_bwd(self, dy, x, name, dres, dx, dxb, drop, modmajor=False):
         st = self.eng.store
         mean, rstd = self.stats[name]
+        if st.has(name + ".scale"):
+            ops.scalenorm_bwd(dy, x, rstd, st.p(name + ".scale"), dres, dx, dxb, drop, st.g(name + ".scale"), R=self.R,
+                              H=self.eng.H)
+            return
         ops.layernorm_bwd(dy, x, mean, rstd, st.p(name + ".weight"), dres, dx, dxb, drop, st.g(name + ".weight"),
                           st.g(name + ".bias"), R=self.R, H=self.eng.H, modmajor_T=self.eng.T if modmajor else 0,
                           S=self.S if modmajor else 0)
@@ -737,6 +746,8 @@ class _StepFn(torch.autograd.Function):
 
 
 class Engine:
+    _created = 0
+
     def __init__(self, model):
         self.model = model
         p0 = next(model.parameters())
@@ -748,9 +759,6 @@ class Engine:
         groups = embedding_groups(model)
         hp = adapter.hyper_params(model, groups)
         self.hp = hp
-        if hp["scalenorm"]:
-            raise NotImplementedError("use_scalenorm=True (mm_utils.py:31-39) is not built in the B200 path; "
-                                      "mm.yaml:41 ships use_scalenorm: false")
         loss_kind = adapter.loss_kinds(model)
         self.H = model.hidden_size
         self.Le, self.Ld = model.n_enc_layers, model.n_dec_layers
@@ -781,10 +789,13 @@ class Engine:
             if self.H // nh not in (32, 64):
                 raise NotImplementedError(f"head size {self.H // nh}: the attention kernels are built for 32 and 64")
         self.T: Optional[int] = None
-        # the step's Philox key (dropout sites + device-side mask sampler), drawn from torch's global generator so that
-        # torch.manual_seed / the trainer's set_seed (utils/utils.py:20-29) select the stream; advanced once per step.
-        # Reseed with engine.reseed(value).
-        self.seed = torch.randint(0, 1 << 62, (1,), dtype=torch.int64).to(self.device)
+        # the step's Philox key (dropout sites + device-side mask sampler): derived from the seed of torch's global
+        # generator, so torch.manual_seed / the trainer's set_seed (utils/utils.py:20-29) select the stream, WITHOUT
+        # drawing from it (the reference Masker's CPU stream must stay untouched for bit-exact masks); engines created
+        # later in the same process get different keys.  Advanced once per step; reseed with engine.reseed(value).
+        Engine._created += 1
+        key = (torch.initial_seed() * 0x9E3779B97F4A7C15 + Engine._created * 0xD1B54A32D192ED03) & 0x3FFFFFFFFFFFFFFF
+        self.seed = torch.tensor([key], dtype=torch.int64, device=self.device)
         self.store = ParamStore(model, self.device)
         self.shadows = Shadows(self.store, model, self.sessions)
         self.plans: Dict[Tuple[int, bool, Any, Tuple[str, ...]], Plan] = {}

@@ -168,11 +168,22 @@ def _fixup(module: nn.Module, n_layers: int) -> None:
                 param.copy_(f * (param * (2 ** 0.5)))
 
 
+class ScaleNorm(nn.Module):
+    """mm_utils.py:31-39: y = x * scale / max(||x||, eps) with ONE learned scalar (parameter container; the arithmetic
+    is mmfm_scalenorm_fwd / _bwd)."""
+
+    def __init__(self, scale, eps=1e-5):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale))
+        self.eps = eps
+
+    def forward(self, x):
+        _only_via_model("ScaleNorm")
+
+
 def _norm(config):
-    if cfg_get(config, "use_scalenorm"):
-        raise NotImplementedError("use_scalenorm=True (mm_utils.py:31-39) is not built in the B200 path; "
-                                  "mm.yaml:41 ships use_scalenorm: false")
-    return nn.LayerNorm(cfg_get(config, "hidden_size"))
+    H = cfg_get(config, "hidden_size")
+    return ScaleNorm(H ** 0.5) if cfg_get(config, "use_scalenorm") else nn.LayerNorm(H)
 
 
 class EncoderLayer(nn.Module):
@@ -258,7 +269,10 @@ class MultiModal(nn.Module):
         self.decoder = nn.ModuleList([DecoderLayer(idx, dtr) for idx in range(self.n_dec_layers)])
         self.decoder_norm = nn.LayerNorm(self.hidden_size)
         # mm.py:79-82; extra single-channel behaviour streams default to MSE (BASELINE config 5 extension)
+        # (a categorical stream -- choice / block, BASELINE.json north_star; the reference has none -- takes 'ce': one-hot
+        # inputs through the ordinary embedder, K-way logits out, masked cross-entropy; pass loss_kinds={'choice': 'ce'})
         self.loss_kind = {m: ("poisson" if m == "ap" else "mse") for m in avail_mod}
+        self.loss_kind.update(kwargs.get("loss_kinds") or {})
 
         self._engine = None
 
@@ -328,6 +342,7 @@ class MultiSessionMultiModal(MultiModal):
 
 def build_model(n_neurons: int, n_behaviors: int, config, avail_mod=("ap", "behavior"), extra_channels=None,
                 **kwargs) -> MultiModal:
+    # kwargs: loss_kinds={modality: 'poisson' | 'mse' | 'ce'} overrides the reference's two defaults (mm.py:79-82)
     """Mirror of train_multi_modal.py:160-189: per-modality embedders then the model."""
     enc, dec = {}, {}
     chan = {m: (n_neurons if m == "ap" else n_behaviors) for m in avail_mod}

@@ -218,6 +218,19 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dxb, drop: DropSpec, dgamm
                                            + (2 if dxb is not None else 0))})
 
 
+def scalenorm_fwd(x, g, y, rnorm, *, R: int, H: int, eps: float = 1e-5) -> None:
+    _launch("mmfm_scalenorm_fwd", x.data_ptr(), g.data_ptr(), y.data_ptr(), rnorm.data_ptr(), R, H, eps,
+            meta={"bytes": 6.0 * R * H})
+
+
+def scalenorm_bwd(dy, x, rnorm, g, dres, dx, dxb, drop: DropSpec, dg, *, R: int, H: int, eps: float = 1e-5) -> None:
+    d = drop.c()
+    _launch("mmfm_scalenorm_bwd", dy.data_ptr(), x.data_ptr(), rnorm.data_ptr(), g.data_ptr(), _p(dres), _p(dx), _p(dxb),
+            C.byref(d), _p(dg), R, H, eps, keep=(d,),
+            meta={"bytes": float(R) * H * (2 + 4 + (4 if dres is not None else 0) + (4 if dx is not None else 0)
+                                           + (2 if dxb is not None else 0))})
+
+
 def _attn_args(q, k, v, o, lse, key_valid, *, B, n_heads, Sq, Sk, d_head, mask_mode, mod_q=None, mod_k=None,
                drop_p: DropSpec = NO_DROP, drop_o: DropSpec = NO_DROP, p_keep=None, d_o=None, delta=None, dq=None,
                dk=None, dv=None) -> AttnArgs:

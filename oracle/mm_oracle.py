@@ -93,6 +93,9 @@ def _linear(P: Mapping[str, torch.Tensor], name: str, x: torch.Tensor) -> torch.
 
 
 def _layer_norm(P, name: str, x: torch.Tensor) -> torch.Tensor:
+    if name + ".scale" in P:
+        # ScaleNorm (mm_utils.py:31-39, use_scalenorm): x * scale / max(||x||, eps), eps 1e-5
+        return x * (P[name + ".scale"] / torch.norm(x, dim=-1, keepdim=True).clamp(min=1e-5))
     # nn.LayerNorm(H), eps 1e-5, affine (encoder_embeddings.py:98,100; mm.py:72,77)
     return F.layer_norm(x, (x.shape[-1],), P[name + ".weight"], P[name + ".bias"], 1e-5)
 
@@ -250,6 +253,11 @@ def forward(P: Mapping[str, torch.Tensor], spec: OracleSpec, batch: Mapping[str,
         w = batch[m]["mask"].unsqueeze(-1).expand(tgt.shape)                  # mm.py:229
         if spec.loss_kind[m] == "poisson":                                    # mm.py:80: exp(p) - t*p
             ell = torch.exp(preds) - tgt * preds
+        elif spec.loss_kind[m] == "ce":
+            # categorical stream (choice / block; extension -- the reference has no CE): the loss
+            # module slotted into mm.py:229-231 unchanged returns the per-element field -t_k * log_softmax(p)_k, so the
+            # masked sum is the token cross-entropy and the divisor is the expanded mask count like everywhere else
+            ell = -(tgt * torch.log_softmax(preds, dim=-1))
         else:                                                                 # mm.py:81
             ell = (preds - tgt) ** 2
         mod_loss[m] = (ell * w).sum()                                         # mm.py:230

@@ -14,7 +14,7 @@ from _util import cosine, load_small, oracle_batch, oracle_params, rel_l2, small
 
 pytestmark = pytest.mark.gpu
 
-LOSS_RTOL, PRED_ATOL, GRAD_RL2, GRAD_COS = 2e-3, 3e-2, 3e-2, 0.999
+LOSS_RTOL, PRED_ATOL, GRAD_RL2, GRAD_COS = 2e-3, 3e-2, 2e-2, 0.999
 
 
 def _mod_dict(spikes, target, attn, ts, masks, dev="cuda"):
@@ -82,6 +82,8 @@ def test_step_matches_reference_golden(mode):
     (dict(decoder_sep_mask=True), 64, 2, 20, False),
     (dict(), 96, 3, 10, True),                                   # train(): all six dropout sites on
     (dict(hidden_size=512, n_heads=8, inter_size=1024, n_layers=2), 128, 2, 0, True),   # d_head 64
+    (dict(use_scalenorm=True, n_layers=2), 64, 3, 10, False),    # ScaleNorm layers (mm_utils.py:31-39)
+    (dict(use_scalenorm=True, n_layers=2), 64, 3, 0, True),
 ])
 def test_step_matches_oracle(cfg_kw, N, B, pad, dropout):
     from multi_modal_foundation_model_b200.config import default_model_config
@@ -300,3 +302,54 @@ def test_compact_eval_masks_equal_dense():
     md = make_mod_dict(batch, ["ap", "behavior"], "encoding", device="cuda")
     two_d = {m: dict(d, eval_mask=d["eval_mask"][:, :, 0].contiguous()) for m, d in md.items()}
     assert model(two_d).loss.item() == model(md).loss.item()
+
+
+def test_choice_block_modalities_cross_entropy_match_oracle():
+    """BASELINE.json north_star: choice / block streams with a CE reconstruction loss (an extension -- the reference has
+    no categorical modality; the oracle's 'ce' branch is pinned to the re-parameterised reference classes in
+    tests/test_oracle_golden.py).  One-hot inputs through the ordinary small-channel embedders, K-way logits out, fused
+    masked cross-entropy + gradient (MMFM_LOSS_CE)."""
+    from multi_modal_foundation_model_b200.config import default_model_config
+    from multi_modal_foundation_model_b200.losses import one_hot_stream
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.synthetic import make_batch
+    from oracle import mm_oracle as orc
+    mods = ["ap", "behavior", "choice", "block"]
+    K = {"choice": 2, "block": 3}
+    cfg = default_model_config(n_layers=2, n_modality=4)
+    torch.manual_seed(13)
+    B, T, N = 6, 100, 72
+    model = build_model(N, 2, cfg, avail_mod=tuple(mods), extra_channels=K, loss_kinds={m: "ce" for m in K})
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    W = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().eval()
+    batch = make_batch(B, N, 2, T, step=6, pad_bins=10)
+    g = torch.Generator().manual_seed(2)
+    xs = {"ap": batch["spikes_data"], "behavior": batch["target"]}
+    for m, k in K.items():
+        xs[m] = one_hot_stream(torch.randint(0, k, (B, 1), generator=g).expand(B, T), k)
+    masks = {m: (torch.rand(B, T, generator=g) < 0.4).long() for m in mods}
+    md = {}
+    for i, m in enumerate(mods):
+        md[m] = dict(inputs=xs[m].cuda(), targets=xs[m].cuda(), inputs_attn_mask=batch["time_attn_mask"].cuda(),
+                     inputs_timestamp=batch["spikes_timestamps"].cuda(), inputs_modality=torch.tensor(i, device="cuda"),
+                     masking_mode=None, eval_mask=masks[m].cuda()[:, :, None].contiguous(),
+                     inputs_regions=np.array([["CA1"] * N] * B))
+    out = model(md)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    spec = orc.OracleSpec.from_config(cfg, mods)
+    spec.loss_kind.update({m: "ce" for m in K})
+    ob = {m: dict(inputs=xs[m], targets=xs[m], attn_mask=batch["time_attn_mask"], timestamp=batch["spikes_timestamps"],
+                  mask=masks[m] & batch["time_attn_mask"]) for m in mods}
+    ref, grads = orc.forward_backward(oracle_params(W), spec, ob)
+    assert abs(out.loss.item() - ref.loss.item()) <= LOSS_RTOL * abs(ref.loss.item()), (out.loss.item(), ref.loss.item())
+    for m in mods:
+        assert int(out.mod_n_examples[m]) == int(ref.mod_n_examples[m])
+        assert abs(out.mod_loss[m].item() - ref.mod_loss[m].item()) <= 3e-3 * abs(ref.mod_loss[m].item()) + 1e-3, m
+        err = (out.mod_preds[m].detach().cpu() - ref.mod_preds[m].detach()).abs().max().item()
+        assert err < PRED_ATOL, (m, err)
+    _check_grads(model, grads, "choice/block CE")

@@ -188,3 +188,23 @@ def test_masker_every_mode_bit_exact_vs_reference_golden():
         for call in range(3):
             got = mk.sample_token_mask(shape, "cpu", regions).numpy()
             assert (got == z[f"case{i}"][call]).all(), (mode, i, call)
+
+
+def test_heldout_mask_compact_form_equals_reference():
+    """eval_masks.heldout_mask == the reference's heldout_mask (eval_utils.py:988-1045, golden from the
+    unmodified function) in every mode: masked spikes, held-out indices, the dense eval mask and the (B,T) column the
+    model reads (mm.py:269-270)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_heldout_golden as gh
+    from multi_modal_foundation_model_b200.eval_masks import heldout_mask
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "heldout.npz"))
+    spikes, regions = gh.inputs()
+    for i, (mode, kw) in enumerate(gh.CASES):
+        r = heldout_mask(spikes.clone(), mode=mode, neuron_regions=regions, **kw)
+        assert np.array_equal(r["spikes"].numpy(), z[f"case{i}/spikes"]), (mode, i)
+        assert np.array_equal(np.asarray(r["heldout_idxs"]).astype(np.int64), z[f"case{i}/hd"]), (mode, i)
+        dense = r["dense_eval_mask"]().numpy()
+        assert np.array_equal(dense, z[f"case{i}/eval_mask"]), (mode, i)
+        assert r["eval_mask"].dtype == torch.int64 and np.array_equal(r["eval_mask"].numpy(), dense[:, :, 0]), (mode, i)
