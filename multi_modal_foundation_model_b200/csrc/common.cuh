@@ -97,6 +97,24 @@ MMFM_DEVINL void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint6
       : "memory");
 }
 
+// Tensor store: one box from shared memory (TMA layout, same swizzle as the map) to global memory; rows / columns
+// outside the tensor are clipped.  Completion is tracked by the issuing thread's bulk async-group.
+MMFM_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+MMFM_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the SOURCE (shared memory) of all but the newest N committed bulk groups has been read
+template <int N>
+MMFM_DEVINL void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+MMFM_DEVINL void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Multicast load: the box lands at the same shared-memory offset of every CTA of the cluster whose rank bit is set in
 // `mask`, and completes `bytes` on the mbarrier at the same offset in each of them.
 MMFM_DEVINL void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {

@@ -742,6 +742,9 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+namespace mmfm {
+int try_launch_gemm_ts(const mmfm_gemm_args* a, cudaStream_t st);   // gemm_ts.cu
+}
 using namespace mmfm;
 
 template <int BN, int STAGES, int EPI>
@@ -832,6 +835,12 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   MMFM_REQUIRE(a->act == MMFM_ACT_NONE || (a->drop.thresh == 0 && a->row_zero == nullptr),
                "mmfm_gemm_tn: an activation epilogue cannot be combined with dropout / token zeroing");
   cudaStream_t st = (cudaStream_t)stream;
+  // calls without output-row remap go to the TMA-store kernel (gemm_ts.cu); the rest (embedding projection with
+  // remap + token zeroing, narrow N, unaligned pitches, legacy activation flavours) stay here
+  {
+    const int taken = try_launch_gemm_ts(a, st);
+    if (taken != 0) return taken > 0 ? 0 : taken;
+  }
   switch (pick_epi(a)) {
     case EPI_PLAIN_BF16: return launch_tn_bn<EPI_PLAIN_BF16>(a, st);
     case EPI_PLAIN_F32: return launch_tn_bn<EPI_PLAIN_F32>(a, st);

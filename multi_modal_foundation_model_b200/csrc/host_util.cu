@@ -35,23 +35,35 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint32_t esize, uint64_t rows,
+                        uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz);
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, ld, box_cols, box_rows, swz);
+}
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                     uint32_t box_rows, TmaSwizzle swz) {
+  return make_tmap_2d(out, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, ld, box_cols, box_rows, swz);
+}
+
+static int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, uint32_t esize, uint64_t rows,
+                        uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   MMFM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   MMFM_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base %p not 16-byte aligned", base);
-  MMFM_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch %llu elements is not a multiple of 16 bytes",
+  MMFM_REQUIRE((ld * esize) % 16 == 0, "TMA row pitch %llu elements is not a multiple of 16 bytes",
                (unsigned long long)ld);
   MMFM_REQUIRE(box_rows <= 256 && box_cols <= 256, "TMA box too large");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * 2};
+  cuuint64_t gstr[1] = {ld * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle s = swz == TMA_SW_128  ? CU_TENSOR_MAP_SWIZZLE_128B
                          : swz == TMA_SW_64 ? CU_TENSOR_MAP_SWIZZLE_64B
                          : swz == TMA_SW_32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMFM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,

@@ -36,6 +36,10 @@ enum TmaSwizzle { TMA_SW_NONE = 0, TMA_SW_32 = 1, TMA_SW_64 = 2, TMA_SW_128 = 3 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz);
 
+// Same for fp32 matrices (epilogue residual loads / output stores of the TMA-store GEMM).
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                     uint32_t box_rows, TmaSwizzle swz);
+
 int device_sm_count();
 
 }  // namespace mmfm
