@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMFM_ABI_VERSION 2
+#define MMFM_ABI_VERSION 3
 
 const char* mmfm_last_error(void);
 int mmfm_abi_version(void);
@@ -50,7 +50,11 @@ enum mmfm_act {
   MMFM_ACT_DSOFTSIGN = 4, /* D <- v * act_scale * (1-|aux/act_scale|)^2   (backward of encoder_embeddings.py:52) */
   MMFM_ACT_GELU_DG = 5,   /* D <- gelu_erf(v); D2 <- gelu_erf'(v): the derivative is saved instead of the pre-activation
                              (erf and the Gaussian term are shared), so the backward epilogue is one multiply */
-  MMFM_ACT_MULAUX = 6     /* D <- v * aux                           (backward of MMFM_ACT_GELU_DG) */
+  MMFM_ACT_MULAUX = 6,    /* D <- v * aux                           (backward of MMFM_ACT_GELU_DG) */
+  MMFM_ACT_ROWDOT_DROP = 7 /* out-projection dgrad fused with the attention-backward preparation (autograd of
+                             mm_utils.py:111-114): rowdot[(r / S) * G + g][r % S] <- sum over the 32 columns of group g of
+                             v * aux  (= delta of head g: rowsum(dO * O)), then D <- dropout(v) (the output-dropout mask
+                             of the forward, args->drop).  N % 32 == 0, d_head == 32 (one head = one column group); bf16 D */
 };
 
 typedef struct mmfm_gemm_args {
@@ -72,6 +76,8 @@ typedef struct mmfm_gemm_args {
   /* optional [S] flags: token position p = remap_off + r % remap_T (or r % remap_S when remap_T == 0) is zeroed
    * before `res` is added (mm.py:147-149,169-171) */
   const unsigned char* row_zero;
+  /* MMFM_ACT_ROWDOT_DROP side output: fp32 [M / rowdot_S, N / 32, rowdot_S] (the attention kernels' delta[B, h, Sq]) */
+  float* rowdot; int rowdot_S;
 } mmfm_gemm_args;
 
 /* D = epilogue(A . B^T).  Replaces nn.Linear forward (mm_utils.py:51-52,107-109,114,145-147,152;
@@ -139,6 +145,9 @@ typedef struct mmfm_attn_args {
   void* dq; long long lddq;
   void* dk; long long lddk;
   void* dv; long long lddv;
+  /* backward: non-zero = `delta` is already filled and `d_o` already carries the output-dropout mask (both produced by
+   * the out-projection dgrad GEMM, MMFM_ACT_ROWDOT_DROP); the preparation kernel is skipped */
+  int prep_done;
 } mmfm_attn_args;
 int mmfm_attention_fwd(const mmfm_attn_args* args, void* stream);
 int mmfm_attention_bwd(const mmfm_attn_args* args, void* stream);

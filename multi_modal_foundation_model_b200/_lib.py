@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xptxas", "-v"]
 
 MAX_MOD = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 MASK_SITE = 8192
 
 
@@ -89,6 +89,7 @@ class GemmArgs(C.Structure):
         ("drop", Dropout),
         ("remap_T", C.c_int), ("remap_S", C.c_int), ("remap_off", C.c_int),
         ("row_zero", C.c_void_p),
+        ("rowdot", C.c_void_p), ("rowdot_S", C.c_int),
     ]
 
 
@@ -111,6 +112,7 @@ class AttnArgs(C.Structure):
         ("dq", C.c_void_p), ("lddq", C.c_longlong),
         ("dk", C.c_void_p), ("lddk", C.c_longlong),
         ("dv", C.c_void_p), ("lddv", C.c_longlong),
+        ("prep_done", C.c_int),
     ]
 
 
@@ -134,7 +136,7 @@ class CastItem(C.Structure):
     ]
 
 
-ACT_NONE, ACT_GELU, ACT_SOFTSIGN, ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU_DG, ACT_MULAUX = 0, 1, 2, 3, 4, 5, 6
+ACT_NONE, ACT_GELU, ACT_SOFTSIGN, ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU_DG, ACT_MULAUX, ACT_ROWDOT_DROP = 0, 1, 2, 3, 4, 5, 6, 7
 MASK_KEY, MASK_KEY_OR_DIAG, MASK_CAUSAL = 0, 1, 2
 LOSS_POISSON, LOSS_MSE, LOSS_CE = 0, 1, 2
 

@@ -1293,9 +1293,11 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
   int pgrid = (int)((R + 7) / 8);
   const int cap = device_sm_count() * 8;
   if (pgrid > cap) pgrid = cap;
-  if (a->d_head == 32) attn_bwd_prep_kernel<32><<<pgrid, 256, 0, st>>>(p);
-  else attn_bwd_prep_kernel<64><<<pgrid, 256, 0, st>>>(p);
-  MMFM_CHECK_CUDA(cudaGetLastError());
+  if (!a->prep_done) {   // else: delta and the masked d_o come from the out-projection dgrad GEMM (MMFM_ACT_ROWDOT_DROP)
+    if (a->d_head == 32) attn_bwd_prep_kernel<32><<<pgrid, 256, 0, st>>>(p);
+    else attn_bwd_prep_kernel<64><<<pgrid, 256, 0, st>>>(p);
+    MMFM_CHECK_CUDA(cudaGetLastError());
+  }
 
   const bool al16 = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
                       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->d_o) |

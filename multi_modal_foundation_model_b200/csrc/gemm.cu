@@ -825,14 +825,17 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   MMFM_REQUIRE(a != nullptr, "mmfm_gemm_tn: null args");
   MMFM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "mmfm_gemm_tn: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   MMFM_REQUIRE(a->A && a->B && a->D, "mmfm_gemm_tn: null operand");
-  MMFM_REQUIRE(a->act >= MMFM_ACT_NONE && a->act <= MMFM_ACT_MULAUX, "mmfm_gemm_tn: bad act %d", a->act);
-  MMFM_REQUIRE(!(a->act == MMFM_ACT_DGELU || a->act == MMFM_ACT_DSOFTSIGN || a->act == MMFM_ACT_MULAUX) || a->aux,
+  MMFM_REQUIRE(a->act >= MMFM_ACT_NONE && a->act <= MMFM_ACT_ROWDOT_DROP, "mmfm_gemm_tn: bad act %d", a->act);
+  MMFM_REQUIRE(!(a->act == MMFM_ACT_DGELU || a->act == MMFM_ACT_DSOFTSIGN || a->act == MMFM_ACT_MULAUX ||
+                 a->act == MMFM_ACT_ROWDOT_DROP) || a->aux,
                "mmfm_gemm_tn: act %d needs aux", a->act);
+  MMFM_REQUIRE(a->act != MMFM_ACT_ROWDOT_DROP || (a->rowdot && a->rowdot_S > 0 && a->M % a->rowdot_S == 0),
+               "mmfm_gemm_tn: MMFM_ACT_ROWDOT_DROP needs rowdot / rowdot_S with M %% rowdot_S == 0");
   MMFM_REQUIRE(a->act != MMFM_ACT_GELU_DG || a->D2, "mmfm_gemm_tn: MMFM_ACT_GELU_DG needs the D2 buffer");
   MMFM_REQUIRE(a->drop.thresh == 0 || a->drop.seed, "mmfm_gemm_tn: dropout without seed pointer");
   MMFM_REQUIRE(a->drop.thresh < 256, "mmfm_gemm_tn: dropout threshold out of range");
   MMFM_REQUIRE(!(a->row_zero && a->remap_T == 0) || a->remap_S > 0, "mmfm_gemm_tn: row_zero needs remap_S");
-  MMFM_REQUIRE(a->act == MMFM_ACT_NONE || (a->drop.thresh == 0 && a->row_zero == nullptr),
+  MMFM_REQUIRE(a->act == MMFM_ACT_NONE || a->act == MMFM_ACT_ROWDOT_DROP || (a->drop.thresh == 0 && a->row_zero == nullptr),
                "mmfm_gemm_tn: an activation epilogue cannot be combined with dropout / token zeroing");
   cudaStream_t st = (cudaStream_t)stream;
   // calls without output-row remap go to the TMA-store kernel (gemm_ts.cu); the rest (embedding projection with
@@ -840,6 +843,9 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   {
     const int taken = try_launch_gemm_ts(a, st);
     if (taken != 0) return taken > 0 ? 0 : taken;
+    MMFM_REQUIRE(a->act != MMFM_ACT_ROWDOT_DROP,
+                 "mmfm_gemm_tn: MMFM_ACT_ROWDOT_DROP is built for the TMA-store kernel only (bf16 D, N %% 32 == 0, N > 64, "
+                 "16-byte aligned D / aux / pitches, no remap / bias)");
   }
   switch (pick_epi(a)) {
     case EPI_PLAIN_BF16: return launch_tn_bn<EPI_PLAIN_BF16>(a, st);

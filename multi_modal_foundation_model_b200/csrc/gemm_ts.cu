@@ -62,13 +62,14 @@ enum TsEpi : int {
   TS_RES = 3,        // D(f32)  = res + dropout(v)
   TS_GELU_DG = 4,    // D(bf16) = gelu(v) ; D2(bf16) = gelu'(v)
   TS_MULAUX = 5,     // D(bf16) = v * aux
-  TS_DSOFTSIGN = 6   // D(bf16) = v * s * (1 - |aux / s|)^2
+  TS_DSOFTSIGN = 6,  // D(bf16) = v * s * (1 - |aux / s|)^2
+  TS_ROWDOT = 7      // rowdot[(r / S), group, r % S] = sum_32cols v * aux ; D(bf16) = dropout(v)   (attention-backward prep)
 };
 
 template <int EPI>
 struct TsCfg {
   static constexpr bool kF32 = EPI == TS_F32 || EPI == TS_RES;
-  static constexpr bool kHasIn = EPI == TS_RES || EPI == TS_MULAUX || EPI == TS_DSOFTSIGN;
+  static constexpr bool kHasIn = EPI == TS_RES || EPI == TS_MULAUX || EPI == TS_DSOFTSIGN || EPI == TS_ROWDOT;
   static constexpr bool kTwoOut = EPI == TS_GELU_DG;
   static constexpr uint32_t kRowBytes = kF32 ? 128u : 64u;          // one box row: 32 columns
   static constexpr uint32_t kSlice = 128u * kRowBytes;              // one [128 x 32] box
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
     const int row = quad * 32 + lane;
     bool drop = false;
     unsigned long long seed = 0ull;
-    if (EPI == TS_RES) {
+    if (EPI == TS_RES || EPI == TS_ROWDOT) {
       drop = p.drop.thresh != 0u;
       if (drop) seed = *p.drop.seed;
     }
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
         uint8_t* box = stg_ptr + sb * Cfg::kBuf + h * Cfg::kSlice + row_off;
         const uint32_t t_row = tmem_base + buf * kTsBN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(128 * hh + 32 * h);
         const long long r = (long long)m0 + row;
+        float dot = 0.f;       // TS_ROWDOT: <v, aux> over this thread's 32 columns (= one attention head at d_head 32)
 #pragma unroll
         for (int c0 = 0; c0 < 32; c0 += 16) {
           uint32_t acc[16];
@@ -344,9 +346,27 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 16; ++j) gelu_erf_both(v[j], v[j], d2[j]);
             }
+            uint4 wdrop = make_uint4(0u, 0u, 0u, 0u);
+            if (EPI == TS_ROWDOT && drop)
+              wdrop = drop_bytes16(seed, p.drop.site, (uint64_t)r, drop_gpr, (uint32_t)((nb + c0) >> 4));
 #pragma unroll
             for (int q8 = 0; q8 < 2; ++q8) {
               uint4* q = reinterpret_cast<uint4*>(box + ((((uint32_t)(c0 >> 3) + q8) ^ swz) << 4));
+              if (EPI == TS_ROWDOT) {
+                const uint4 a4 = *q;                                  // attention output O, in place
+                const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 a2 = unpack_bf16x2(aw[e]);
+                  dot = fmaf(v[8 * q8 + 2 * e], a2.x, dot);
+                  dot = fmaf(v[8 * q8 + 2 * e + 1], a2.y, dot);
+                }
+                if (drop) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    v[8 * q8 + e] = (drop_byte(wdrop, 8 * q8 + e) < p.drop.thresh) ? 0.f : v[8 * q8 + e] * p.drop.scale;
+                }
+              }
               if (EPI == TS_MULAUX || EPI == TS_DSOFTSIGN) {
                 const uint4 a4 = *q;                                  // saved tensor, in place
                 const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
@@ -371,6 +391,11 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
                                pack_bf16x2(d2[8 * q8 + 4], d2[8 * q8 + 5]), pack_bf16x2(d2[8 * q8 + 6], d2[8 * q8 + 7]));
             }
           }
+        }
+        if (EPI == TS_ROWDOT && r < p.M) {
+          const long long bb = r / p.rowdot_S;
+          const int ii = (int)(r - bb * p.rowdot_S);
+          p.rowdot[(bb * (p.N >> 5) + (nb >> 5)) * p.rowdot_S + ii] = dot;
         }
       }
       // staged box over to the store warp; after the last unit the accumulator buffer goes back to the MMA warp
@@ -500,7 +525,7 @@ int try_launch_gemm_ts(const mmfm_gemm_args* a, cudaStream_t st) {
     if (a->act != MMFM_ACT_NONE || !f32 || a->D2 || !al16(a->res) || (a->ldr * 4) % 16 != 0) return 0;
     epi = TS_RES;
   } else {
-    if (drop) return 0;
+    if (drop && a->act != MMFM_ACT_ROWDOT_DROP) return 0;
     switch (a->act) {
       case MMFM_ACT_NONE:
         if (a->D2) return 0;
@@ -519,6 +544,11 @@ int try_launch_gemm_ts(const mmfm_gemm_args* a, cudaStream_t st) {
         if (f32 || a->D2 || !a->aux || !al16(a->aux) || (a->ldaux * 2) % 16 != 0) return 0;
         epi = a->act == MMFM_ACT_MULAUX ? TS_MULAUX : TS_DSOFTSIGN;
         break;
+      case MMFM_ACT_ROWDOT_DROP:
+        if (f32 || a->D2 || a->bias || !a->aux || !al16(a->aux) || (a->ldaux * 2) % 16 != 0 || a->N % 32 != 0 || !a->rowdot)
+          return 0;
+        epi = TS_ROWDOT;
+        break;
       default:
         return 0;
     }
@@ -532,6 +562,7 @@ int try_launch_gemm_ts(const mmfm_gemm_args* a, cudaStream_t st) {
     case TS_GELU_DG: rc = launch_ts<TS_GELU_DG>(a, st); break;
     case TS_MULAUX: rc = launch_ts<TS_MULAUX>(a, st); break;
     case TS_DSOFTSIGN: rc = launch_ts<TS_DSOFTSIGN>(a, st); break;
+    case TS_ROWDOT: rc = launch_ts<TS_ROWDOT>(a, st); break;
     default: return 0;
   }
   return rc == 0 ? 1 : rc;

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import adapter, masker as _masker, ops
-from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_SOFTSIGN, LOSS_CE, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
+from ._lib import (ACT_DGELU, ACT_DSOFTSIGN, ACT_GELU, ACT_GELU_DG, ACT_MULAUX, ACT_NONE, ACT_ROWDOT_DROP, ACT_SOFTSIGN, LOSS_CE, LOSS_MSE, LOSS_POISSON, MASK_CAUSAL,
                    MASK_KEY, MASK_KEY_OR_DIAG, CastItem, MmfmError, lib)
 from .ops import NO_DROP, DropSpec
 
@@ -406,7 +406,7 @@ class Plan:
 
     # ---------------------------------------------------------------------------------------------------
     def _attention(self, fwd: bool, tag: str, q, k, v, o, mode, nh, p_drop, kind_p, kind_o, layer, side, sep,
-                   grads=None):
+                   grads=None, prep_done=False):
         B, S, H = self.B, self.S, self.eng.H
         d = H // nh
         if fwd:
@@ -423,7 +423,7 @@ class Plan:
         else:
             d_o, dq, dk, dv = grads
             ops.attention_bwd(q, k, v, o, self.lse[tag], self.kvalid, d_o=d_o, delta=self.delta, dq=dq, dk=dk, dv=dv,
-                              **kw)
+                              prep_done=prep_done, **kw)
 
     # ---------------------------------------------------------------------------------------------------
     def _build_forward(self, f32, b16):
@@ -580,10 +580,11 @@ class Plan:
             off = st.total if next_param is None else st.offset[st.alias[next_param]]
             self.grad_marks.append((len(rec.calls), off))
 
-        def lin_bwd(dY, X, wname, shadow_key, dX, *, act=ACT_NONE, aux=None, act_scale=1.0, wnames=None, bnames=None):
+        def lin_bwd(dY, X, wname, shadow_key, dX, *, act=ACT_NONE, aux=None, act_scale=1.0, wnames=None, bnames=None,
+                    **extra):
             """dX = dY . W ; dW += dY^T X ; db += colsum(dY)"""
             if dX is not None:
-                ops.gemm_tn(dY, sh.tr[shadow_key], dX, act=act, aux=aux, act_scale=act_scale)
+                ops.gemm_tn(dY, sh.tr[shadow_key], dX, act=act, aux=aux, act_scale=act_scale, **extra)
             bn = bnames or [wname + ".bias"]
             ops.gemm_wgrad(dY, X, self._wgrad_dst(wnames or [wname + ".weight"]),
                            dbias=self._bias(bn, "g") if st.has(bn[0]) else None)
@@ -595,12 +596,24 @@ class Plan:
             lin_bwd(duv, A[ln_name], pre + ".up_proj", pre + ".up_proj", dh)
             self._ln_bwd(dh, x_in, ln_name, Gs, Gs, dxb, drop_prev)
 
+        def out_proj_bwd(pre, nh, p_drop, kind_o, layer, side):
+            """out-projection dgrad (+ wgrad).  At d_head 32 its epilogue also does the attention-backward preparation
+            (delta = rowsum(dO * O) per head, output-dropout mask on dO): one launch and one pass over dO / O less per
+            attention call.  Returns True when the attention kernel may skip its own preparation."""
+            fuse = eng.fuse_attn_prep and H // nh == 32
+            if fuse:
+                lin_bwd(Gb, A[pre + ".ao"], pre + ".out_proj", pre + ".out_proj", d_ao, act=ACT_ROWDOT_DROP,
+                        aux=A[pre + ".ao"], rowdot=self.delta, rowdot_S=S, drop=self._drop(kind_o, layer, side, p_drop))
+            else:
+                lin_bwd(Gb, A[pre + ".ao"], pre + ".out_proj", pre + ".out_proj", d_ao)
+            return fuse
+
         def attn_bwd(pre, x_in, ln_name, Gs, mode, nh, p_drop, layer, side, sep, dxb, drop_prev):
-            lin_bwd(Gb, A[pre + ".ao"], pre + ".out_proj", pre + ".out_proj", d_ao)
+            fused = out_proj_bwd(pre, nh, p_drop, SITE_ATTN_OUT, layer, side)
             qkv = A[pre + ".qkv"]
             self._attention(False, pre, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], A[pre + ".ao"], mode, nh, p_drop,
                             SITE_ATTN_PROB, SITE_ATTN_OUT, layer, side, sep,
-                            grads=(d_ao, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]))
+                            grads=(d_ao, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]), prep_done=fused)
             lin_bwd(dqkv, A[ln_name], None, pre + ".qkv", dh,
                     wnames=[f"{pre}.{k}.weight" for k in ("query", "key", "value")],
                     bnames=[f"{pre}.{k}.bias" for k in ("query", "key", "value")])
@@ -627,10 +640,10 @@ class Plan:
             y0, y1, y2, y3 = self.ys[3 * i: 3 * i + 4]
             mlp_bwd(pre + ".mlp", y2, pre + ".ln2", G, eng.dec_inter, Gb, NO_DROP)
             xa = pre + ".cross_attn"
-            lin_bwd(Gb, A[xa + ".ao"], xa + ".out_proj", xa + ".out_proj", d_ao)
+            fused = out_proj_bwd(xa, hp["dec_heads"], hp["dec_dropout"], SITE_XATTN_OUT, i, SIDE_DEC)
             self._attention(False, xa, A[xa + ".q"], A[xa + ".kv"][:, :H], A[xa + ".kv"][:, H:], A[xa + ".ao"],
                             MASK_KEY_OR_DIAG, hp["dec_heads"], hp["dec_dropout"], SITE_XATTN_PROB, SITE_XATTN_OUT, i,
-                            SIDE_DEC, False, grads=(d_ao, dqx, dkvx[:, :H], dkvx[:, H:]))
+                            SIDE_DEC, False, grads=(d_ao, dqx, dkvx[:, :H], dkvx[:, H:]), prep_done=fused)
             lin_bwd(dqx, A[pre + ".query_norm"], xa + ".query", xa + ".query", dh)
             self._ln_bwd(dh, y1, pre + ".query_norm", G, G, Gb, NO_DROP)
             lin_bwd(dkvx, A[pre + ".context_norm"], None, xa + ".kv", dh,
@@ -805,6 +818,10 @@ class Engine:
         self.use_graphs = _os.environ.get("MMFM_CUDA_GRAPHS", "1") != "0"
         # MLP forward saves gelu'(u) (default) or the pre-activation u (MMFM_GELU_SAVE=u: A/B of the two backward epilogues)
         self.save_gelu_grad = _os.environ.get("MMFM_GELU_SAVE", "dg") != "u"
+        # attention-backward preparation inside the out-projection dgrad epilogue (MMFM_FUSE_ATTN_PREP=0: separate kernel);
+        # needs the TMA-store GEMM, i.e. H > 64
+        self.fuse_attn_prep = (_os.environ.get("MMFM_FUSE_ATTN_PREP", "1") != "0" and self.H > 64 and self.H % 32 == 0
+                               and _os.environ.get("MMFM_GEMM_TS", "1") != "0")
         self.last_plan: Optional[Plan] = None
         self._grad_views = None
         from .model import MultiModalOutput

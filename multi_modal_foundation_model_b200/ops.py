@@ -111,7 +111,8 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, M: Optional[in
             D2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, act: int = ACT_NONE,
             act_scale: float = 1.0, drop: DropSpec = NO_DROP, remap: Tuple[int, int, int] = (0, 0, 0),
             row_zero: Optional[torch.Tensor] = None, lda: Optional[int] = None, ldb: Optional[int] = None,
-            ldd: Optional[int] = None, ldr: Optional[int] = None, ldaux: Optional[int] = None) -> None:
+            ldd: Optional[int] = None, ldr: Optional[int] = None, ldaux: Optional[int] = None,
+            rowdot: Optional[torch.Tensor] = None, rowdot_S: int = 0) -> None:
     """D = epilogue(A . B^T); A [M,K] bf16, B [N,K] bf16 (row pitches from the tensors unless given)."""
     assert A.dtype == bf16 and B.dtype == bf16 and D.dtype in (bf16, torch.float32)
     a = GemmArgs()
@@ -134,6 +135,9 @@ def gemm_tn(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, M: Optional[in
     a.drop = drop.c()
     a.remap_T, a.remap_S, a.remap_off = remap
     a.row_zero = _p(row_zero)
+    if rowdot is not None:
+        assert rowdot.dtype == torch.float32 and rowdot_S > 0
+    a.rowdot, a.rowdot_S = _p(rowdot), int(rowdot_S)
     mn = float(a.M) * a.N
     nbytes = 2.0 * a.M * a.K + 2.0 * a.N * a.K + mn * (4 if a.d_fp32 else 2)      # algorithmic: A + B + D ...
     nbytes += (2.0 * mn if D2 is not None else 0.0) + (4.0 * mn if res is not None else 0.0) + (2.0 * mn if aux is not None else 0.0)
@@ -233,7 +237,7 @@ def scalenorm_bwd(dy, x, rnorm, g, dres, dx, dxb, drop: DropSpec, dg, *, R: int,
 
 def _attn_args(q, k, v, o, lse, key_valid, *, B, n_heads, Sq, Sk, d_head, mask_mode, mod_q=None, mod_k=None,
                drop_p: DropSpec = NO_DROP, drop_o: DropSpec = NO_DROP, p_keep=None, d_o=None, delta=None, dq=None,
-               dk=None, dv=None) -> AttnArgs:
+               dk=None, dv=None, prep_done: bool = False) -> AttnArgs:
     a = AttnArgs()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
     a.k, a.ldk = k.data_ptr(), k.stride(0)
@@ -253,6 +257,7 @@ def _attn_args(q, k, v, o, lse, key_valid, *, B, n_heads, Sq, Sk, d_head, mask_m
         a.dq, a.lddq = dq.data_ptr(), dq.stride(0)
         a.dk, a.lddk = dk.data_ptr(), dk.stride(0)
         a.dv, a.lddv = dv.data_ptr(), dv.stride(0)
+    a.prep_done = 1 if prep_done else 0
     return a
 
 
@@ -270,7 +275,7 @@ def attention_bwd(q, k, v, o, lse, key_valid, **kw) -> None:
     fused = a.d_head == 32 and a.Sq <= 256 and a.Sk <= 256 and not a.mod_q
     _launch("mmfm_attention_bwd", C.byref(a), keep=(a,),
             meta={"flops": 8.0 * a.B * a.n_heads * a.Sq * a.Sk * a.d_head,   # algorithmic: 2x forward
-                  "kernels": 2 if fused else 3})
+                  "kernels": (2 if fused else 3) - (1 if a.prep_done else 0)})
 
 
 def mask_prep(masks: Sequence[Optional[torch.Tensor]], attns: Sequence[torch.Tensor], channels: Sequence[int],

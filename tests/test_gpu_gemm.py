@@ -137,3 +137,28 @@ def test_colsum_and_cast():
     yt = torch.zeros(50, 72, device="cuda", dtype=torch.bfloat16)[:, :70]
     ops.cast_bf16(x, y, yt)
     assert torch.equal(y, x.to(torch.bfloat16)) and torch.equal(yt, x.to(torch.bfloat16).T)
+
+
+@pytest.mark.parametrize("M,S,dropout", [(600, 200, True), (51200, 200, True), (1000, 100, False)])
+def test_gemm_tn_rowdot_dropout_attention_prep(M, S, dropout):
+    """Out-projection dgrad fused with the attention-backward preparation (MMFM_ACT_ROWDOT_DROP): per 32-column group
+    (= head at d_head 32) rowdot[b, g, i] = <v, aux> and D = dropout(v) with the forward's output-dropout stream."""
+    from _util import philox_keep_torch
+    from multi_modal_foundation_model_b200 import ops
+    from multi_modal_foundation_model_b200._lib import ACT_ROWDOT_DROP
+    N, K = 256, 256
+    A, B = _mk(M, K, seed=21, scale=0.3), _mk(N, K, seed=22, scale=0.1)
+    O = _mk(M, N, seed=23)
+    D = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    Bt = M // S
+    delta = torch.full((Bt, N // 32, S), 7.0, device="cuda")
+    seed_val = 0x77AA55
+    seed = torch.tensor([seed_val], dtype=torch.int64, device="cuda")
+    ops.gemm_tn(A, B, D, act=ACT_ROWDOT_DROP, aux=O, rowdot=delta, rowdot_S=S,
+                drop=ops.DropSpec(seed, 4098, 0.4) if dropout else ops.NO_DROP)
+    v = A.float() @ B.float().T
+    ref_delta = (v * O.float()).view(Bt, S, N // 32, 32).sum(-1).permute(0, 2, 1)
+    _close(delta, ref_delta, 3e-3, "rowdot (delta)")
+    if dropout:
+        v = v * philox_keep_torch(seed_val, 4098, M, N, 0.4, "cuda")
+    _close(D, v, 8e-3, "masked dO")
