@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
     int n_items) {
   constexpr int D = 32;
   constexpr uint32_t kSbo64 = 512;
+  pdl_enter();   // the prologue already issues this CTA's first operand loads: wait before anything else
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t ld_bar[2], s_bar[2], dp_bar[2], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -404,9 +405,8 @@ int launch_attn_bwd_persist(const mmfm_attn_args* a, const AttnParams& p, cudaSt
   const int n_items = a->B * a->n_heads;
   int grid = device_sm_count();
   if (grid > n_items) grid = n_items;
-  if (drop) attn_bwd_persist_kernel<true><<<grid, kFusedThreads, kPersistSmem, st>>>(tq, tdo, tk, tv, p, npk, n_items);
-  else attn_bwd_persist_kernel<false><<<grid, kFusedThreads, kPersistSmem, st>>>(tq, tdo, tk, tv, p, npk, n_items);
-  MMFM_CHECK_CUDA(cudaGetLastError());
+  if (drop) MMFM_CHECK_CUDA(launch_pdl(attn_bwd_persist_kernel<true>, dim3(grid), dim3(kFusedThreads), kPersistSmem, st, tq, tdo, tk, tv, p, npk, n_items));
+  else MMFM_CHECK_CUDA(launch_pdl(attn_bwd_persist_kernel<false>, dim3(grid), dim3(kFusedThreads), kPersistSmem, st, tq, tdo, tk, tv, p, npk, n_items));
   return 0;
 }
 }  // namespace mmfm

@@ -30,6 +30,20 @@ MMFM_DEVINL bool elect_one() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch: every hot kernel starts with pdl_enter().  The trigger lets the NEXT kernel of the
+// stream / graph be scheduled while this one is still running (its CTAs become resident as SMs drain and park at their
+// own wait), the wait blocks until every prerequisite grid has completed and its writes are visible -- so kernel-to-
+// kernel launch latency and the tail of a persistent grid overlap instead of adding up.  Without the launch attribute
+// (host_util.h: launch_pdl; off unless MMFM_PDL=1 -- measured neutral on the default step) both instructions are no-ops.
+// ------------------------------------------------------------------------------------------------
+MMFM_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+MMFM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MMFM_DEVINL void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 MMFM_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
   uint32_t nst = bstat ? (STAGES * kStageBytes - b_res_bytes) / kABytes : (uint32_t)STAGES;
   if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -542,6 +544,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   const uint16_t mask_free = (uint16_t)(mask_x | mask_y);      // CTAs whose loads land in this CTA's stages
   const uint32_t n_free = (uint32_t)(1 + (cx == 2) + (cy == 2));
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmY);
     tma_prefetch_desc(&tmX);
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   if (clustered) cluster_sync_all();   // every CTA's barriers are initialised before a peer's multicast can touch them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -781,8 +785,8 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
     grid = per_n * tiles_n;
     bstat = 1;
   }
-  gemm_tn_kernel<BN, STAGES, EPI><<<grid, kTnThreads, smem, st>>>(tmA, tmB, *a, tiles_n, n_tiles, bstat);
-  MMFM_CHECK_CUDA(cudaGetLastError());
+  MMFM_CHECK_CUDA(launch_pdl(gemm_tn_kernel<BN, STAGES, EPI>, dim3(grid), dim3(kTnThreads), smem, st, tmA, tmB, *a, tiles_n,
+                             n_tiles, bstat));
   return 0;
 }
 
@@ -905,13 +909,15 @@ extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, lo
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cx;
   attr[0].val.clusterDim.y = cy;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   MMFM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<STAGES>, tmY, tmX, R, NO, KI, dW, ldw, rows_per_split, dbias,
                                      cx, cy));
   return 0;

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
   const uint32_t stg_base = smem_base + stg_off;                      // staging buffers (1024-aligned)
   uint8_t* stg_ptr = smem_al + stg_off;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();      // barriers / TMEM are set up; from here on global memory of the preceding kernels is touched
 
   if (warp == 0) {
     // ------------------------------------------------ A / B ring producer ------------------------------------------
@@ -473,8 +475,8 @@ static int launch_ts_bn(const mmfm_gemm_args* a, cudaStream_t st) {
     grid = (sms / tiles_n) * tiles_n;
     smem = 1024 + b_res + (size_t)nst * a_stage + 2 * (size_t)Cfg::kBuf;
   }
-  gemm_tn_ts_kernel<EPI, BN><<<grid, kTsThreads, smem, st>>>(tmA, tmB, tmD, tmD2, tmIn, *a, tiles_n, n_tiles, bstat, nst);
-  MMFM_CHECK_CUDA(cudaGetLastError());
+  MMFM_CHECK_CUDA(launch_pdl(gemm_tn_ts_kernel<EPI, BN>, dim3(grid), dim3(kTsThreads), smem, st, tmA, tmB, tmD, tmD2, tmIn, *a,
+                             tiles_n, n_tiles, bstat, nst));
   return 0;
 }
 

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
                                                                        bf16* __restrict__ y, float* __restrict__ mean,
                                                                        float* __restrict__ rstd, int R, int H,
                                                                        float eps, int modmajor_T, int S) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
   const float invH = 1.0f / (float)H;
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
     bf16* __restrict__ dxb, DropCfg drop, float* __restrict__ dgamma, float* __restrict__ dbeta, int R, int H,
     int modmajor_T, int S) {
   static_assert(NV > 0, "register path only");
+  pdl_enter();
   __shared__ float red[kLnWarps][NV * 128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
@@ -374,7 +376,7 @@ extern "C" int mmfm_layernorm_fwd(const float* x, const float* gamma, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ln_grid_fwd(R, H);
 #define LN_FWD(NV) \
-  layernorm_fwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>(x, gamma, beta, (bf16*)y, mean, rstd, R, H, eps, modmajor_T, S)
+  MMFM_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(kLnWarps * 32), 0, st, x, gamma, beta, (bf16*)y, mean, rstd, R, H, eps, modmajor_T, S))
   switch (H) {
     case 128: LN_FWD(1); break;
     case 256: LN_FWD(2); break;
@@ -410,8 +412,8 @@ extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* m
     static int cap = 0;                                                                                           \
     if (cap == 0) cap = resident_ctas(layernorm_bwd_kernel<NV>, kLnWarps * 32);                                   \
     const int grid = want < cap ? (want < 1 ? 1 : want) : cap;                                                    \
-    layernorm_bwd_kernel<NV><<<grid, kLnWarps * 32, 0, st>>>((const bf16*)dy, x, mean, rstd, gamma, dres, dx,     \
-                                                              (bf16*)dxb, dc, dgamma, dbeta, R, H, modmajor_T, S); \
+    MMFM_CHECK_CUDA(launch_pdl(layernorm_bwd_kernel<NV>, dim3(grid), dim3(kLnWarps * 32), 0, st, (const bf16*)dy, x, mean,  \
+                               rstd, gamma, dres, dx, (bf16*)dxb, dc, dgamma, dbeta, R, H, modmajor_T, S));             \
   } while (0)
   switch (H) {
     case 128: LN_BWD(1); break;
