@@ -497,7 +497,11 @@ __global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_con
 // wgrad kernel: dW[NO,KI] += sum over a slice of rows of dY[r,NO]^T X[r,KI];  optionally db[NO] += colsum(dY)
 // (the bias gradient rides on the tensor pipe: one extra N=16 MMA per k-step against a tile of ones)
 // ------------------------------------------------------------------------------------------------
-template <int STAGES>
+// BN = 256 (KI % 256 == 0): one CTA per SM owns a 128 x 256 tile of dW.  As in gemm_ts.cu the main loop is bound by
+// shared-memory bandwidth (every operand byte is written once by TMA and read once by the tensor core; a 128 x 128 x 16
+// MMA alone reads 128 B/clk), and the wider tile moves 25 % fewer bytes per FLOP and reads every dY box once instead of
+// once per 128-column tile.
+template <int STAGES, int BN>
 __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmY,
                                                                    const __grid_constant__ CUtensorMap tmX, int R,
                                                                    int NO, int KI, float* __restrict__ dW,
@@ -507,13 +511,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
   // same rows: the two KI tiles of a cluster row share their dY boxes, the two NO tiles of a cluster column share their
   // X boxes, so each CTA loads HALF of what it consumes and TMA-multicasts it to its peer (this kernel is bound by
   // L2 -> SM traffic: every dY box is needed by all KI tiles and every X box by all NO tiles).
-  constexpr int BN = 128;
   constexpr uint32_t kBoxBytes = 64 * kBK * 2;  // [64 rows(k) x 64 cols(mn)] bf16 = 8 KB
   constexpr uint32_t kABytes = 2 * kBoxBytes;
-  constexpr uint32_t kBBytes = 2 * kBoxBytes;
+  constexpr uint32_t kBBytes = (BN / 64) * kBoxBytes;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kOnesBytes = 2048;         // 16 k-rows x 128 B of bf16(1.0)
-  constexpr uint32_t kTmemCols = 256;           // 128 (dW tile) + 16 (bias column), power of two
+  constexpr uint32_t kTmemCols = 2 * BN;        // BN (dW tile) + 16 (bias column), power of two
   constexpr int kPitch = BN + 4;
   static_assert((size_t)kBM * kPitch * 4 <= (size_t)STAGES * kStageBytes, "staging tile must fit in the stages");
 
@@ -597,8 +600,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
         if (cy == 2) {   // ... and X box yl for both NO tiles of its cluster column
           tma_load_2d_mc(a_dst + kABytes + yl * kBoxBytes, &tmX, &full_bar[s], ki0 + 64 * yl, r0, mask_y);
         } else {
-          tma_load_2d_addr(a_dst + kABytes, &tmX, &full_bar[s], ki0, r0);
-          tma_load_2d_addr(a_dst + kABytes + kBoxBytes, &tmX, &full_bar[s], ki0 + 64, r0);
+#pragma unroll
+          for (int bx = 0; bx < BN / 64; ++bx)
+            tma_load_2d_addr(a_dst + kABytes + bx * kBoxBytes, &tmX, &full_bar[s], ki0 + 64 * bx, r0);
         }
       }
     }
@@ -655,27 +659,30 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_wgrad_kernel(const __grid_c
       if (no0 + row_l < NO) atomicAdd(dbias + no0 + row_l, __uint_as_float(bacc[0]));
     }
     __syncwarp();
-    // coalesced accumulation: lane = 4 consecutive columns, one row per step
-    const int lcol = lane * 4;
-    const int kcol = ki0 + lcol;
-    const int nvalid = KI - kcol;
-    const bool vec = (ldw % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+    // coalesced accumulation: lane = 4 consecutive columns, one row (128 columns of it) per step
+#pragma unroll 1
+    for (int cp = 0; cp < BN / 128; ++cp) {
+      const int lcol = cp * 128 + lane * 4;
+      const int kcol = ki0 + lcol;
+      const int nvalid = KI - kcol;
+      const bool vec = (ldw % 4 == 0) && nvalid >= 4 && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
 #pragma unroll 4
-    for (int it = 0; it < 32; ++it) {
-      const int rl = quad * 32 + it;
-      const int no = no0 + rl;
-      if (no >= NO || nvalid <= 0) continue;
-      const float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
-      float* dst = dW + (long long)no * ldw + kcol;
-      if (vec) {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
-                     "f"(v.w)
-                     : "memory");
-      } else {
-        if (nvalid > 0) atomicAdd(dst, v.x);
-        if (nvalid > 1) atomicAdd(dst + 1, v.y);
-        if (nvalid > 2) atomicAdd(dst + 2, v.z);
-        if (nvalid > 3) atomicAdd(dst + 3, v.w);
+      for (int it = 0; it < 32; ++it) {
+        const int rl = quad * 32 + it;
+        const int no = no0 + rl;
+        if (no >= NO || nvalid <= 0) continue;
+        const float4 v = *reinterpret_cast<const float4*>(stage_f + rl * kPitch + lcol);
+        float* dst = dW + (long long)no * ldw + kcol;
+        if (vec) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                       "f"(v.w)
+                       : "memory");
+        } else {
+          if (nvalid > 0) atomicAdd(dst, v.x);
+          if (nvalid > 1) atomicAdd(dst + 1, v.y);
+          if (nvalid > 2) atomicAdd(dst + 2, v.z);
+          if (nvalid > 3) atomicAdd(dst + 3, v.w);
+        }
       }
     }
   }
@@ -865,24 +872,23 @@ extern "C" int mmfm_gemm_tn(const mmfm_gemm_args* a, void* stream) {
   }
 }
 
-extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI,
-                               float* dW, long long ldw, float* dbias, void* stream) {
-  MMFM_REQUIRE(dY && X && dW, "mmfm_gemm_wgrad: null operand");
-  MMFM_REQUIRE(R > 0 && NO > 0 && KI > 0, "mmfm_gemm_wgrad: bad shape R=%d NO=%d KI=%d", R, NO, KI);
+template <int BN>
+static int launch_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI, float* dW,
+                        long long ldw, float* dbias, void* stream) {
   constexpr int STAGES = 3;
   CUtensorMap tmY, tmX;
   int rc = make_tmap_bf16_2d(&tmY, dY, (uint64_t)R, (uint64_t)NO, (uint64_t)lddy, 64, kBK, TMA_SW_128);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmX, X, (uint64_t)R, (uint64_t)KI, (uint64_t)ldx, 64, kBK, TMA_SW_128);
   if (rc) return rc;
-  constexpr size_t smem = (size_t)STAGES * (4 * 64 * kBK * 2) + 2048 + 1024;
+  constexpr size_t smem = (size_t)STAGES * ((2 + BN / 64) * 64 * kBK * 2) + 2048 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MMFM_CHECK_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<STAGES, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
     attr_set = true;
   }
-  const int tiles = ((NO + kBM - 1) / kBM) * ((KI + 127) / 128);
+  const int tiles = ((NO + kBM - 1) / kBM) * ((KI + BN - 1) / BN);
   const int kblocks = (R + kBK - 1) / kBK;
   static int waves_x2 = -1;   // MMFM_WGRAD_CTAS_X2: target CTA count in half-SM-counts (default 4 = two CTAs per SM)
   if (waves_x2 < 0) {
@@ -892,18 +898,19 @@ extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, lo
   }
   // all CTAs must be resident at once (two per SM): a split count rounded UP spills a few CTAs into a second wave that
   // costs as much as the first (measured 43 us vs 34 us on the QKV shape), so round down
-  int splits = (waves_x2 * device_sm_count() / 2) / tiles;
+  // BN 256: one CTA per SM (144 KB of stages, 512 TMEM columns); BN 128: two
+  int splits = ((BN == 256 ? 2 : waves_x2) * device_sm_count() / 2) / tiles;
   if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   int rows_per_split = ((kblocks + splits - 1) / splits) * kBK;
   splits = (R + rows_per_split - 1) / rows_per_split;
-  dim3 grid((KI + 127) / 128, (NO + kBM - 1) / kBM, splits);
+  dim3 grid((KI + BN - 1) / BN, (NO + kBM - 1) / kBM, splits);
   static int mc_env = -1;   // MMFM_WGRAD_MULTICAST=1: 2x2 clusters, each CTA loads half of its boxes and multicasts them
   if (mc_env < 0) {
     const char* e = getenv("MMFM_WGRAD_MULTICAST");
     mc_env = (e && e[0] == '1') ? 1 : 0;   // measured slower than independent CTAs (lock-step stages): off by default
   }
-  const int cx = (mc_env && grid.x % 2 == 0) ? 2 : 1, cy = (mc_env && grid.y % 2 == 0) ? 2 : 1;
+  const int cx = (mc_env && BN == 128 && grid.x % 2 == 0) ? 2 : 1, cy = (mc_env && BN == 128 && grid.y % 2 == 0) ? 2 : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kGemmThreads);
@@ -918,9 +925,23 @@ extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, lo
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  MMFM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<STAGES>, tmY, tmX, R, NO, KI, dW, ldw, rows_per_split, dbias,
+  MMFM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<STAGES, BN>, tmY, tmX, R, NO, KI, dW, ldw, rows_per_split, dbias,
                                      cx, cy));
   return 0;
+}
+
+
+extern "C" int mmfm_gemm_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int R, int NO, int KI,
+                               float* dW, long long ldw, float* dbias, void* stream) {
+  MMFM_REQUIRE(dY && X && dW, "mmfm_gemm_wgrad: null operand");
+  MMFM_REQUIRE(R > 0 && NO > 0 && KI > 0, "mmfm_gemm_wgrad: bad shape R=%d NO=%d KI=%d", R, NO, KI);
+  static int bn_env = -1;   // MMFM_WGRAD_BN=128 pins the 128-wide dW tile (A/B measurements)
+  if (bn_env < 0) {
+    const char* e = getenv("MMFM_WGRAD_BN");
+    bn_env = e ? atoi(e) : 128;   // the 256-wide tile measured equal (QKV 29.4 vs 29.8 us) to slower (down 25.7 vs 23.4 us)
+  }
+  if (bn_env == 256 && KI % 256 == 0) return launch_wgrad<256>(dY, lddy, X, ldx, R, NO, KI, dW, ldw, dbias, stream);
+  return launch_wgrad<128>(dY, lddy, X, ldx, R, NO, KI, dW, ldw, dbias, stream);
 }
 
 extern "C" int mmfm_colsum_bf16(const void* dY, long long ld, int R, int NO, float* out, void* stream) {
