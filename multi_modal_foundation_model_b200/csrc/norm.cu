@@ -37,19 +37,20 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
   const long long BT = modmajor_T > 0 ? (long long)(R / S) * modmajor_T : 0;
   const float invH = 1.0f / (float)H;
   if constexpr (NV > 0 && NV <= 4) {
-    // register path, two rows per warp in flight: both rows' loads are issued before either reduction starts
-    for (long long r0 = ((long long)blockIdx.x * kLnWarps + warp) * 2; r0 < R; r0 += (long long)gridDim.x * kLnWarps * 2) {
-      const bool two = r0 + 1 < R;
-      float4 v[2][NV];
+    // register path, kLnRows rows per warp in flight: all rows' loads are issued before the first reduction starts
+    // (NV <= 2: four rows, 64 KB in flight per SM at full occupancy -- the two-row form reached 62 % of the HBM peak)
+    constexpr int U = NV <= 2 ? 4 : 2;
+    for (long long r0 = ((long long)blockIdx.x * kLnWarps + warp) * U; r0 < R; r0 += (long long)gridDim.x * kLnWarps * U) {
+      float4 v[U][NV];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int j = 0; j < NV; ++j)
-          v[u][j] = (u == 0 || two) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + u) * H) + lane + 32 * j)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-      float mu[2], rs[2];
+          v[u][j] = (r0 + u < R) ? __ldg(reinterpret_cast<const float4*>(x + (r0 + u) * H) + lane + 32 * j)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      float mu[U], rs[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
@@ -62,10 +63,16 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
         }
         rs[u] = rsqrtf(warp_sum(q) * invH + eps);
       }
+      float4 gm[NV], bt[NV];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !two) break;
+      for (int j = 0; j < NV; ++j) {
+        gm[j] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+        bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         const long long r = r0 + u;
+        if (r >= R) break;
         if (lane == 0) {
           mean[r] = mu[u];
           rstd[r] = rs[u];
@@ -73,11 +80,9 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_kernel(const floa
         bf16* yr = y + ln_out_row(r, modmajor_T, S, BT) * H;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
           uint2 o;
-          o.x = pack_bf16x2((v[u][j].x - mu[u]) * rs[u] * g.x + b.x, (v[u][j].y - mu[u]) * rs[u] * g.y + b.y);
-          o.y = pack_bf16x2((v[u][j].z - mu[u]) * rs[u] * g.z + b.z, (v[u][j].w - mu[u]) * rs[u] * g.w + b.w);
+          o.x = pack_bf16x2((v[u][j].x - mu[u]) * rs[u] * gm[j].x + bt[j].x, (v[u][j].y - mu[u]) * rs[u] * gm[j].y + bt[j].y);
+          o.y = pack_bf16x2((v[u][j].z - mu[u]) * rs[u] * gm[j].z + bt[j].z, (v[u][j].w - mu[u]) * rs[u] * gm[j].w + bt[j].w);
           reinterpret_cast<uint2*>(yr)[lane + 32 * j] = o;
         }
       }
@@ -354,8 +359,9 @@ static int ln_grid(int R) {
   return (R + kLnWarps - 1) / kLnWarps;
 }
 static int ln_grid_fwd(int R, int H) {
-  // H <= 512: two rows per warp (see the kernel), so half the CTAs
-  if (H == 128 || H == 256 || H == 512) return (R + 2 * kLnWarps - 1) / (2 * kLnWarps);
+  // register path: four (H <= 256) or two (H == 512) rows per warp (see the kernel), so fewer CTAs
+  if (H == 128 || H == 256) return (R + 4 * kLnWarps - 1) / (4 * kLnWarps);
+  if (H == 512) return (R + 2 * kLnWarps - 1) / (2 * kLnWarps);
   return ln_grid(R);
 }
 

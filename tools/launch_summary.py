@@ -8,7 +8,7 @@ import re
 import sys
 
 FAMILY = [  # kernel-name regex -> C-ABI family used in bench.py's kernel table
-    (r"gemm_tn_kernel", "mmfm_gemm_tn"), (r"gemm_wgrad_kernel", "mmfm_gemm_wgrad"),
+    (r"gemm_tn(_ts)?_kernel", "mmfm_gemm_tn"), (r"gemm_wgrad_kernel", "mmfm_gemm_wgrad"),
     (r"attn_fwd", "mmfm_attention_fwd"), (r"attn_bwd", "mmfm_attention_bwd"),
     (r"layernorm_fwd", "mmfm_layernorm_fwd"), (r"layernorm_bwd", "mmfm_layernorm_bwd"),
     (r"loss_kernel", "mmfm_loss_fwd_bwd"), (r"adamw", "mmfm_adamw_step"),
