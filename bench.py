@@ -398,6 +398,7 @@ def main():
     from multi_modal_foundation_model_b200.synthetic import DevicePrefetcher
     pf = DevicePrefetcher(dev)
 
+    e2e_compact = [False]     # trainer-form dense int64 eval masks (False) or the compact scalar / (B,T) forms (True)
     host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_losses = []
@@ -410,7 +411,7 @@ def main():
             pf.put(host_batches[i % NB])
         db = pf.get()                                                                                  # H2D of batch i
         pf.put(host_batches[(i + 1) % NB])                                                             # H2D of batch i+1
-        md = make_mod_dict(db, wl.mods, MODES[i % 3], device=dev)
+        md = make_mod_dict(db, wl.mods, MODES[i % 3], device=dev, compact_masks=e2e_compact[0])
         out = model(md)
         out.loss.backward()
         model.zero_grad(set_to_none=True)
@@ -487,9 +488,11 @@ def main():
         fp32_batches = host_batches
         host_batches = [dict(hb, spikes_data=hb["spikes_data"].to(torch.uint8).pin_memory()) for hb in fp32_batches]
         pf._next = None
-        for i in range(3 if not wl.multi else NB):
+        e2e_compact[0] = True          # the wire format of this path: byte counts + compact masks
+        for i in range(6 if not wl.multi else NB):
             step_e2e(i)
         ms_e2e_u8 = timed(step_e2e, a.steps)
+        e2e_compact[0] = False
         h2d_u8 = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v)) for hb in host_batches) // NB
         host_batches = fp32_batches
         pf._next = None
@@ -592,12 +595,18 @@ def main():
             "scaling": "strong" if a.strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfgj, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / a.steps},
+                    "ms_per_step": ms_e2e / a.steps,
+                    "what": "model(mod_dict) + loss.backward() on pinned HOST batches in the reference trainer's own form "
+                            "(fp32 spikes; mod_dict with dense int64 eval masks built as trainer/base.py:51-103 builds it), "
+                            "H2D of every batch and D2H of every loss inside the timed region"},
             "gpu_launches": launches,
             "e2e_uint8_wire": (None if ms_e2e_u8 is None else
                                {"value": B * n_gpus * a.steps / (ms_e2e_u8 / 1e3), "unit": UNIT,
                                 "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 4,
-                                "what": "e2e with spike counts shipped as uint8 and expanded on the device (8f rank 2)"}),
+                                "ms_per_step": ms_e2e_u8 / a.steps,
+                                "what": "the same with this path's wire format: spike counts shipped as uint8 and expanded "
+                                        "on the device, compact eval masks (scalar / (B,T)) instead of dense (B,T,N) int64 "
+                                        "tensors (SURVEY 8f rank 2 / 3)"}),
             "with_optimizer": {"value": value_opt, "unit": UNIT, "ms_per_step": ms_opt / a.steps,
                                "what": "fwd + bwd + fused AdamW step (mmfm_adamw_step over the flat fp32 buffers)"},
             "sustained": sustained, "library_bar": libbar,

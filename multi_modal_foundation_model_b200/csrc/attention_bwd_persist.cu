@@ -18,6 +18,17 @@
 #include "attn_common.cuh"
 #include <stdlib.h>
 
+#ifdef MMFM_DBG_TIMING
+// globaltimer trace of one item of one CTA (tools/micro/bwd_persist_timing.py)
+__device__ long long g_dbg_bp[64];
+#define DBG_BP(slot) do { if (blockIdx.x == 7 && it == 3 && threadIdx.x == 32) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) :: "memory"); g_dbg_bp[slot] = t_; } } while (0)
+extern "C" int mmfm_debug_read_bwd_persist(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_dbg_bp, sizeof(long long) * 64);
+}
+#else
+#define DBG_BP(slot) do { } while (0)
+#endif
+
 namespace mmfm {
 
 constexpr uint32_t kPRow = 64;                       // bytes per operand row (32 bf16), 64-byte swizzle
@@ -165,8 +176,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
       const uint32_t m = __ballot_sync(0xffffffffu, v);
       if (lane == 0) s_colbits[w] = m;
     }
+    DBG_BP(0);
     mbar_wait(&ld_bar[st], (uint32_t)((it >> 1) & 1));   // operands + side data of this item have landed
     __syncthreads();
+    DBG_BP(1);
     if (it == 0 && warp == 0) {
       if (elect_one()) {
         tc_fence_after();
@@ -210,8 +223,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
       for (int kh = 0; kh < 2; ++kh) {
         if (kh >= nkh) break;
         const int c = grp + 4 * kh;
+        DBG_BP(4 + 16 * qt + 4 * kh);
         mbar_wait(&s_bar[kh], par);
         tc_fence_after();
+        DBG_BP(5 + 16 * qt + 4 * kh);
         if (c < nch) {
           const uint32_t aw = aws[kh];
           uint32_t km[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
@@ -248,9 +263,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
             }
           }
         }
+        DBG_BP(6 + 16 * qt + 4 * kh);
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        DBG_BP(7 + 16 * qt + 4 * kh);
         if (warp == 0) {
           if (elect_one()) {
             tc_fence_after();
@@ -265,8 +282,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
       for (int kh = 0; kh < 2; ++kh) {
         if (kh >= nkh) break;
         const int c = grp + 4 * kh;
+        DBG_BP(12 + 16 * qt + 4 * kh);
         mbar_wait(&dp_bar[kh], par);   // dP_h is there, and the dV product has finished reading this half's slabs
         tc_fence_after();
+        DBG_BP(13 + 16 * qt + 4 * kh);
         if (c < nch) {
           const uint32_t aw = aws[kh];
           const bool masked = __any_sync(0xffffffffu, aw != 0xFFFFFFFFu);
@@ -292,9 +311,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
             }
           }
         }
+        DBG_BP(14 + 16 * qt + 4 * kh);
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
+        DBG_BP(15 + 16 * qt + 4 * kh);
         if (warp == 0) {
           if (elect_one()) {
             tc_fence_after();
@@ -317,8 +338,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
     // ---------------- read-out: 16-column pieces over the 4 thread groups ----------------
     //   piece 0..3   : dQ of query tile piece/2, column half piece&1          (TMEM lane = query row)
     //   piece 4..11  : (kh, which, half) = ((piece-4)/4, ((piece-4)/2)&1, (piece-4)&1); which 0 dK, 1 dV (lane = key row)
+    DBG_BP(40);
     mbar_wait(&done_bar, (uint32_t)(it & 1));
     tc_fence_after();
+    DBG_BP(41);
     uint32_t r[3][16];
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
@@ -357,6 +380,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
                        pack_bf16x2(__uint_as_float(r[u][k + 6]) * fs, __uint_as_float(r[u][k + 7]) * fs));
     }
     __syncthreads();   // staged; also: every thread has its accumulators out of TMEM before the next item's products
+    DBG_BP(42);
 #pragma unroll 1
     for (int k6 = 0; k6 < 6; ++k6) {
       const int idx = k6 * kFusedThreads + tid;      // (tile, row, 16-byte piece)
@@ -374,6 +398,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) attn_bwd_persist_kernel(
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(stage_o + (tile * 128 + rr) * kOutPitch + q4 * 16);
     }
     __syncthreads();   // the staging area becomes the next item's P_drop slabs; side data / stage st are retired
+    DBG_BP(43);
   }
 
   tc_fence_before();

@@ -71,8 +71,10 @@ class AdamW(torch.optim.Optimizer):
             st.adopt()
         g = self.param_groups[0]
         # gradients must be the flat buffer's views (engine.backward installs them); anything else is copied in
+        skipped = []     # parameters without a gradient: torch.optim.AdamW leaves them (weights, moments, step) untouched
         for n, p in st.params.items():
             if p.grad is None:
+                skipped.append((n, st.p(n).clone(), st.view(self._m, n).clone(), st.view(self._v, n).clone()))
                 st.g(n).zero_()
             elif p.grad.data_ptr() != st.g(n).data_ptr():
                 st.g(n).copy_(p.grad)
@@ -80,8 +82,14 @@ class AdamW(torch.optim.Optimizer):
         b1, b2 = g["betas"]
         ops.adamw_step(st.flat, st.grad, self._m, self._v, lr=g["lr"], beta1=b1, beta2=b2, eps=g["eps"],
                        weight_decay=g["weight_decay"], step=self._steps)
-        for s in self.state.values():
-            s["step"] += 1
+        for n, w, m, v in skipped:      # the one launch covers the whole flat buffer: put the skipped ranges back
+            st.p(n).copy_(w)
+            st.view(self._m, n).copy_(m)
+            st.view(self._v, n).copy_(v)
+        skip = {id(st.params[n]) for n, *_ in skipped}
+        for q, s in self.state.items():
+            if id(q) not in skip:
+                s["step"] += 1
         return loss
 
     def load_state_dict(self, state_dict):

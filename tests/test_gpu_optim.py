@@ -54,3 +54,27 @@ def test_adamw_requires_engine_parameters():
     w.grad = torch.ones_like(w)
     with pytest.raises(MmfmError):
         AdamW([w]).step()
+
+
+def test_adamw_leaves_parameters_without_gradient_untouched():
+    """torch.optim.AdamW skips a parameter whose .grad is None (no update, no weight decay, no moment decay); the fused
+    step covers the whole flat buffer in one launch and must put such ranges back."""
+    from multi_modal_foundation_model_b200.model import build_model
+    from multi_modal_foundation_model_b200.optim import AdamW
+    from multi_modal_foundation_model_b200.synthetic import make_batch, make_mod_dict
+    torch.manual_seed(2)
+    model = build_model(40, 2, small_config()).cuda().eval()
+    opt = AdamW(model.parameters(), lr=1e-2, weight_decay=0.1, eps=1e-8)
+    md = lambda: make_mod_dict(make_batch(3, 40, 2, 100, step=0), ["ap", "behavior"], "encoding", device="cuda")
+    model(md()).loss.backward()
+    opt.step()                                        # builds the moments
+    model(md()).loss.backward()
+    name, frozen = "encoder.0.mlp.up_proj.weight", dict(model.named_parameters())["encoder.0.mlp.up_proj.weight"]
+    w0 = frozen.detach().clone()
+    m0 = opt.state[frozen]["exp_avg"].clone()
+    other = dict(model.named_parameters())["encoder.0.mlp.down_proj.weight"]
+    o0 = other.detach().clone()
+    frozen.grad = None
+    opt.step()
+    assert torch.equal(frozen.detach(), w0) and torch.equal(opt.state[frozen]["exp_avg"], m0), name
+    assert not torch.equal(other.detach(), o0)
