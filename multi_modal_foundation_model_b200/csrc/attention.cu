@@ -1278,8 +1278,10 @@ static int launch_bwd_fused2(const mmfm_attn_args* a, const AttnParams& p, cudaS
 }
 
 // Backward dispatch (after the prep kernel: delta = rowsum(dO * O), dO <- dO * output-dropout mask):
-//   d_head 32, Sq, Sk <= 256 (the default model)  -> persistent fused kernel (attention_bwd_persist.cu), or its
-//                                                     one-CTA-per-(batch, head) form when the side data are unaligned
+//   d_head 32, Sq, Sk <= 256 (the default model)  -> persistent warp-specialised fused kernel (attention_bwd_ws.cu;
+//                                                     MMFM_ATTN_WS=0: its block-synchronous predecessor
+//                                                     attention_bwd_persist.cu), or the one-CTA-per-(batch, head) form
+//                                                     when the side data are unaligned
 //   any other shape without modality-separation    -> streamed tcgen05 dq / dkv pair (attention_bwd_stream.cu)
 //   modality-separation mask, odd alignments        -> mma.sync dq / dkv pair
 extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
@@ -1303,11 +1305,12 @@ extern "C" int mmfm_attention_bwd(const mmfm_attn_args* a, void* stream) {
                       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->d_o) |
                       reinterpret_cast<uintptr_t>(a->dq) | reinterpret_cast<uintptr_t>(a->dk) |
                       reinterpret_cast<uintptr_t>(a->dv)) & 15) == 0;
-  static int tc_bwd = -1, fused = -1, persist = -1, streamed = -1;
+  static int tc_bwd = -1, fused = -1, persist = -1, streamed = -1, ws = -1;
   const bool tc = attn_tc_enabled() && env_on("MMFM_ATTN_TC_BWD", &tc_bwd) && a->mod_q == nullptr && al16;
   if (tc && env_on("MMFM_ATTN_FUSED_BWD", &fused) && a->d_head == 32 && a->Sq <= 256 && a->Sk <= 256) {
     const bool side_al = ((reinterpret_cast<uintptr_t>(a->lse) | reinterpret_cast<uintptr_t>(a->delta) |
                            reinterpret_cast<uintptr_t>(a->p_keep)) & 15) == 0 && a->Sq % 4 == 0;
+    if (env_on("MMFM_ATTN_WS", &ws) && side_al) return launch_attn_bwd_ws(a, p, st);
     if (env_on("MMFM_ATTN_PERSIST", &persist) && side_al) return launch_attn_bwd_persist(a, p, st);
     return launch_bwd_fused2(a, p, st);
   }

@@ -124,5 +124,7 @@ int launch_attn_fwd_pipe(const mmfm_attn_args* a, const AttnParams& p, cudaStrea
 int launch_attn_bwd_stream(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
 // attention_bwd_persist.cu: persistent software-pipelined fused backward (d_head 32, Sq, Sk <= 256, Sq % 4 == 0)
 int launch_attn_bwd_persist(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
+// attention_bwd_ws.cu: the same data flow, warp-specialised (issuer / loader warps, deferred read-out, TMA stores)
+int launch_attn_bwd_ws(const mmfm_attn_args* a, const AttnParams& p, cudaStream_t st);
 
 }  // namespace mmfm

@@ -66,6 +66,13 @@ MMFM_DEVINL void mbar_arrive(uint64_t* bar) {
 #ifndef MMFM_MBAR_HINT_NS
 #define MMFM_MBAR_HINT_NS 20000
 #endif
+// polls before a waiter gives up: with the suspend hint one poll lasts up to MMFM_MBAR_HINT_NS, so 2^17 polls are a few
+// seconds (a protocol bug must not hold a GPU box for minutes)
+#if MMFM_MBAR_HINT_NS > 0
+#define MMFM_MBAR_SPIN_LIMIT (1u << 17)
+#else
+#define MMFM_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 MMFM_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
 #if MMFM_MBAR_HINT_NS > 0
@@ -94,9 +101,9 @@ MMFM_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++n > (1u << 26)) {
-      printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
+    if (++n > MMFM_MBAR_SPIN_LIMIT) {
+      printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u bar %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity, smem_u32(bar));
       __trap();
     }
   }
@@ -107,9 +114,9 @@ MMFM_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(40);
-    if (++n > (1u << 25)) {
-      printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, parity);
+    if (++n > MMFM_MBAR_SPIN_LIMIT) {
+      printf("mmfm: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u bar %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, parity, smem_u32(bar));
       __trap();
     }
   }
@@ -133,6 +140,11 @@ MMFM_DEVINL void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint6
 MMFM_DEVINL void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(smem_src),
                "r"(c0), "r"(c1)
+               : "memory");
+}
+MMFM_DEVINL void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_src),
+               "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 MMFM_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -395,6 +407,29 @@ MMFM_DEVINL float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work)
+MMFM_DEVINL uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+MMFM_DEVINL void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+MMFM_DEVINL uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+MMFM_DEVINL uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+MMFM_DEVINL uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 // ------------------------------------------------------------------------------------------------
 // warp-level mma.sync path (attention core: d_head 32/64 tiles are softmax-bound)

@@ -72,6 +72,30 @@ static int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType 
   return 0;
 }
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  MMFM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  MMFM_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base %p not 16-byte aligned", base);
+  MMFM_REQUIRE((ld * 2) % 16 == 0, "TMA row pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)ld);
+  MMFM_REQUIRE(box_rows <= 256 && box_cols <= 256, "TMA box too large");
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstr[2] = {ld * 2, rows * ld * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle s = swz == TMA_SW_128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                         : swz == TMA_SW_64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                         : swz == TMA_SW_32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                            : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMFM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-d) failed (%d) batch=%llu rows=%llu cols=%llu ld=%llu box=%ux%u",
+               (int)r, (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols,
+               (unsigned long long)ld, box_cols, box_rows);
+  return 0;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

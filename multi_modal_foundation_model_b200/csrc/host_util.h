@@ -40,6 +40,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                      uint32_t box_rows, TmaSwizzle swz);
 
+// 3-D bf16 tensor map over [batch][rows][cols] (row pitch `ld` elements, batch pitch rows * ld): a box never crosses a
+// batch entry, so rows past `rows` are clipped on store / zero-filled on load.  box = box_cols x box_rows x 1.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows, TmaSwizzle swz);
+
 int device_sm_count();
 
 // MMFM_PDL=1 (default 0: measured neutral): launch the hot kernels with programmatic stream serialization (see
