@@ -14,8 +14,20 @@
 //   * masked / unmasked template copies of every pass (68 KB of SASS for a 32 KB instruction cache) -> one copy; a
 //     chunk that carries a mask first overwrites its masked scores in registers
 // Roles (576 threads): warps 0-15 math (thread = query row = TMEM lane; warp quadrant x four 32-key column groups),
-// warp 16 tcgen05.mma issuer, warp 17 TMA loader / storer.  (18 warps x 112 registers fill the register file; a 640-thread
-// form with setmaxnreg cannot give the math warps more: the launch allocation is 96 per thread and the pool is per CTA.)
+// warp 16 tcgen05.mma issuer, warp 17 TMA loader / storer.  Two schedulers host five warps, so ptxas caps the kernel at
+// 96 registers per thread.
+//
+// Measured on B200 (tools/attn_bench.py, default shape, dropout on, preparation kernel included): 201 us for the block-
+// synchronous kernel -> 141 us (this structure) -> 135 us with the issuer's MMA batches unrolled (a rolled loop spends
+// ~100 clocks of descriptor arithmetic per 41-clock MMA: tools/micro/umma_rate.cu).  What a globaltimer trace of this
+// kernel (tools/micro/bwd_ws_timing.py) shows per item: probability passes at the MUFU bound (0.54 us per 128 x 128
+// block = 16 exp2 per clock and SM), dS passes ~0.42 us, and about as much again in hand-over latency between passes.
+// Variants that were built, verified and measured SLOWER, so they are not here: eight math warps with 168 registers
+// (147 us: one or two warps per scheduler cannot cover the MUFU / tcgen05.ld latencies); two column groups that own one
+// key half each and run one pass out of phase, with 8 or 16 math warps (157 - 187 us: same reason); 8-key work units dealt
+// evenly to the column groups (the predicated unit bodies cost more instructions than the balance wins); setmaxnreg
+// (the register pool only holds what a warpgroup released: the math warps cannot get past 112, and a 32-register issuer
+// spills inside its MMA batches).
 #include "attn_common.cuh"
 #include <stdlib.h>
 
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           for (int k = 0; k < D / 16; ++k)
             umma_bf16(tmem_base + 128u * kh, make_smem_desc(ad + k * 32, 16, kSbo64, 4),
                       make_smem_desc(bv + k * 32, 16, kSbo64, 4), idesc, k > 0 ? 1u : 0u);
-#pragma unroll 1
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_bf16(tmem_base + dvc + 32u * kh,
                       make_smem_desc(sSlab + (uint32_t)(2 * kh) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
@@ -177,14 +189,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           const uint32_t base = smem_base + st * kWStage;
           const int nks = (kh == nkh - 1 ? wlast : 128) >> 4;
           const uint32_t aq = base + 2 * kWOp + (uint32_t)qt * 128u * kWRow;
-#pragma unroll 1
+#pragma unroll 8
           for (int k2 = 0; k2 < nks; ++k2) {
             const int kk = 8 * kh + k2;           // 16-key step inside the whole key range
             umma_bf16(tmem_base + dq_col + 32u * qt,
                       make_smem_desc(sSlab + (uint32_t)(kk >> 2) * kSlabBytes + (uint32_t)(kk & 3) * 32u, 16, 1024, 2),
                       make_smem_desc(base + (uint32_t)kk * 16u * kWRow, kSbo64, kSbo64, 4), idesc_q, (kh > 0 || k2 > 0) ? 1u : 0u);
           }
-#pragma unroll 1
+#pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_bf16(tmem_base + dk_col + 32u * kh,
                       make_smem_desc(sSlab + (uint32_t)(2 * kh) * kSlabBytes + (uint32_t)kk * 2048u, kSlabBytes, 1024, 2),
@@ -320,6 +332,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
         const uint32_t par = ph & 1u;
         const int i = qt * 128 + row;
         const bool rok = i < p.Sq;
+        // a warp whose 32 query rows all lie past Sq (S = 200: the last quadrant of the second tile) only zeroes its part
+        // of the slabs: the probability passes are MUFU-bound, so every dead row skipped is time won
+        const bool dead = qt * 128 + quad * 32 >= p.Sq;
         float lse2 = INFINITY, ndl = 0.f;
         if (rok) {
           const float l = s_lse[i];
@@ -351,7 +366,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           mbar_wait(&s_bar[kh], par);
           tc_fence_after();
           DBG_WS(5 + 16 * qt + 4 * kh);
-          if (c < nch) {
+          if (c < nch && dead) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              st_shared_v4(slab_row + (uint32_t)(c >> 1) * kSlabBytes + ((((uint32_t)((c & 1) * 4 + q4)) ^ swz) << 4), 0u, 0u, 0u, 0u);
+          } else if (c < nch) {
             uint32_t rs[32];
             tmem_ld32(t_row + 32u * c, rs);
             uint32_t km[4][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
@@ -407,7 +426,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           mbar_wait(&dp_bar[kh], par);   // dP_h is there, and the dV product has finished reading this half's slabs
           tc_fence_after();
           DBG_WS(13 + 16 * qt + 4 * kh);
-          if (c < nch) {
+          if (c < nch && !dead) {          // (a dead warp's slab rows already hold zeros = its dS)
             uint32_t rd[32];
             tmem_ld32(t_row + 32u * c, rd);
             const uint32_t aw = aws[kh];
