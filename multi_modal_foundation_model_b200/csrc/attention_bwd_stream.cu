@@ -39,7 +39,7 @@ MMFM_DEVINL void keep_words(const uint2 w2, int c, uint32_t (&kw)[4]) {
 template <int D, bool DROP>
 __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dq_stream_kernel(
     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int nb) {
+    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p, int nb_all) {
   using Cfg = StreamCfg<D>;
   constexpr uint32_t kRowBytes = Cfg::kRowBytes, kLayout = Cfg::kLayout, kSbo = Cfg::kSbo;
   extern __shared__ uint8_t smem_raw[];
@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dq_stream_kernel(
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int mode = p.mask_mode;
   const long long bh = (long long)(b * p.nh + h);
-  const int bl = ((p.Sk - (nb - 1) * 128) + 15) & ~15;   // width of the last key block
+  // mask-aware block skipping: under the causal mask the keys after this query tile's last row are never attended, so the
+  // key blocks past the diagonal are neither loaded nor multiplied (half of all blocks for a long sequence)
+  const int nb = (mode == MMFM_MASK_CAUSAL) ? min(nb_all, q0 / 128 + 1) : nb_all;
+  const int bl = (nb == nb_all) ? (((p.Sk - (nb - 1) * 128) + 15) & ~15) : 128;   // width of the last key block
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -249,6 +252,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
   const int nkb = (p.Sk + kTile - 1) / kTile;
   const float dsc = DROP ? p.drop_p.scale : 1.0f;
   const int bl = ((p.Sq - (nbq - 1) * 128) + 15) & ~15;   // width of the last query block
+  // mask-aware block skipping: under the causal mask the queries before this key tile never attend it, so the loop starts
+  // at the diagonal block (stages / barrier phases count from there)
+  const int blk0 = (mode == MMFM_MASK_CAUSAL) ? min(k0 / 128, nbq - 1) : 0;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -261,10 +267,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
     mbar_arrive_expect_tx(&ld_kv, 2 * Cfg::kTile);
     tma_load_2d_addr(sK, &tmK, &ld_kv, h * D, b * p.Sk + k0);
     tma_load_2d_addr(sV, &tmV, &ld_kv, h * D, b * p.Sk + k0);
-    for (int s = 0; s < 2 && s < nbq; ++s) {
+    for (int s = 0; s < 2 && blk0 + s < nbq; ++s) {
       mbar_arrive_expect_tx(&q_full[s], 2 * Cfg::kTile);
-      tma_load_2d_addr(sQd + 2 * s * Cfg::kTile, &tmQ, &q_full[s], h * D, b * p.Sq + s * 128);
-      tma_load_2d_addr(sQd + (2 * s + 1) * Cfg::kTile, &tmdO, &q_full[s], h * D, b * p.Sq + s * 128);
+      tma_load_2d_addr(sQd + 2 * s * Cfg::kTile, &tmQ, &q_full[s], h * D, b * p.Sq + (blk0 + s) * 128);
+      tma_load_2d_addr(sQd + (2 * s + 1) * Cfg::kTile, &tmdO, &q_full[s], h * D, b * p.Sq + (blk0 + s) * 128);
     }
   }
   if (warp == 1) {
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
       }
     }
   };
-  if (tid < 128) stage_rows(0, 0, tid);
+  if (tid < 128) stage_rows(blk0, 0, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,8 +301,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
   constexpr uint32_t dp_col = 128u, acc_col = 256u;
 
   auto issue_scores = [&](int blk) {   // S^T = K Q_i^T, dP^T = V dO_i^T  (one elected thread)
-    const int s = blk & 1;
-    mbar_wait(&q_full[s], (uint32_t)((blk >> 1) & 1));
+    const int s = (blk - blk0) & 1;
+    mbar_wait(&q_full[s], (uint32_t)(((blk - blk0) >> 1) & 1));
     tc_fence_after();
     const uint32_t n = (uint32_t)(blk == nbq - 1 ? bl : 128);
     const uint32_t idesc = make_idesc_bf16(128, n, 0, 0);
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
   if (warp == 0) {
     if (elect_one()) {
       mbar_wait(&ld_kv, 0);
-      issue_scores(0);
+      issue_scores(blk0);
     }
     __syncwarp();
   }
@@ -331,16 +337,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
   const uint32_t idesc_acc = make_idesc_bf16(128, D, 0, 1);
 
 #pragma unroll 1
-  for (int blk = 0; blk < nbq; ++blk) {
+  for (int blk = blk0; blk < nbq; ++blk) {
     const int width = (blk == nbq - 1) ? bl : 128;
-    const int st = blk & 1;
+    const int st = (blk - blk0) & 1;
     const int c = grp;                        // this thread's 32-query chunk of the block
     const bool mine = 32 * c < width;
-    mbar_wait(&m1_bar, (uint32_t)(blk & 1));
+    mbar_wait(&m1_bar, (uint32_t)((blk - blk0) & 1));
     tc_fence_after();
     // block blk-1's dK / dV products finished before these scores: its Q / dO stage is free -> fetch block blk+1
-    if (tid == 0 && blk >= 1 && blk + 1 < nbq) {
-      const int s = (blk + 1) & 1;
+    if (tid == 0 && blk > blk0 && blk + 1 < nbq) {
+      const int s = (blk + 1 - blk0) & 1;
       mbar_arrive_expect_tx(&q_full[s], 2 * Cfg::kTile);
       tma_load_2d_addr(sQd + 2 * s * Cfg::kTile, &tmQ, &q_full[s], h * D, b * p.Sq + (blk + 1) * 128);
       tma_load_2d_addr(sQd + (2 * s + 1) * Cfg::kTile, &tmdO, &q_full[s], h * D, b * p.Sq + (blk + 1) * 128);
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) attn_bwd_dkv_stream_kernel(
         const int nks = width >> 4;
         for (int kk = 0; kk < nks; ++kk) {
           const uint32_t a_off = 32u * (kk >> 1) + 8u * (kk & 1);
-          const uint32_t acc = (blk > 0 || kk > 0) ? 1u : 0u;
+          const uint32_t acc = (blk > blk0 || kk > 0) ? 1u : 0u;
           umma_bf16_ts(tmem_base + acc_col, tmem_base + a_off,
                        make_smem_desc(aq + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc_acc, acc);
           umma_bf16_ts(tmem_base + acc_col + D, tmem_base + dp_col + a_off,

@@ -172,11 +172,25 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
 
   // item -> (b, h, q0): query-tile pair fastest, then head, then batch
   auto decode = [&](int item, int& b, int& h, int& q0) {
-    const int qp = item % n_qp;
-    const int bh = item / n_qp;
-    h = bh % p.nh;
+    int bh = item;
+    q0 = 0;
+    if (n_qp > 1) {                 // (the default model has one tile pair per (batch, head): no division for it)
+      bh = item / n_qp;
+      // the pair index is rotated by bh: with a grid that is a multiple of n_qp a CTA would otherwise always get the same
+      // pair position, and under the causal mask (blocks walked grow with q0) the CTAs of the last position set the time
+      q0 = ((item - bh * n_qp + bh) % n_qp) * 256;
+    }
     b = bh / p.nh;
-    q0 = qp * 256;
+    h = bh - b * p.nh;
+  };
+  // Mask-aware block skipping: under the causal mask the keys after a tile's last query row are never attended, so a
+  // tile only walks the key blocks up to its diagonal (tile A of a pair one block fewer than tile B) and the producer
+  // only loads those -- half of all score blocks of a long sequence.  Number of key blocks tile X of the pair at q0 uses:
+  const bool causal_skip = p.mask_mode == MMFM_MASK_CAUSAL && nb > 1;
+  auto tile_blocks = [&](int q0, int X) -> int {
+    const int r0 = q0 + 128 * X;
+    if (r0 >= p.Sq) return 0;
+    return causal_skip ? min(nb, (r0 + 127) / bn + 1) : nb;
   };
 
   if (warp == kTmaWarp) {
@@ -209,8 +223,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
         __syncwarp();
         if (lane == 0) mbar_arrive(&q_full[qs]);
       }
+      const int nst = max(tile_blocks(q0, 0), tile_blocks(q0, 1));   // key blocks any tile of this pair needs
       if (lane == 0) {
-        for (int j = 0; j < nb; ++j) {
+        for (int j = 0; j < nst; ++j) {
           const int ks = (t + j) % kKvStages;
           mbar_wait_relaxed(&kv_empty[ks], (uint32_t)((((t + j) / kKvStages) & 1) ^ 1));
           mbar_arrive_expect_tx(&kv_full[ks], 2u * (uint32_t)bn * kRowBytes);
@@ -218,28 +233,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
           tma_load_2d_addr(sKV + ks * Cfg::kKvStage + Cfg::kKvHalf, &tmV, &kv_full[ks], h * D, b * p.Sk + j * bn);
         }
       }
-      t += nb;
+      t += nst;
       __syncwarp();
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------ MMA issuer --------------------------------------------------
     if (elect_one()) {
       const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const int nsteps = my_items * nb;
       const uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);   // A = P (TMEM, K-major), B = V MN-major
-      uint32_t cnt[2] = {0u, 0u};                                // steps issued per tile (barrier phases)
+      uint32_t cnt[2] = {0u, 0u};                                // blocks issued per tile (barrier phases)
 
-      auto has_tile = [&](int step, int X) -> bool {
-        if (X == 0) return true;
-        int b, h, q0;
-        decode((int)blockIdx.x + (step / nb) * (int)gridDim.x, b, h, q0);
-        return q0 + 128 < p.Sq;
-      };
-      auto issue_qk = [&](int step, int X) {
-        const int it = step / nb, j = step - it * nb;
-        const int qs = it & 1, ks = step % kKvStages;
+      // S of (item it, key block j, tile X) from K/V ring step t
+      auto issue_qk = [&](int it, int j, int X, int t) {
+        const int qs = it & 1, ks = t % kKvStages;
         mbar_wait_relaxed(&q_full[qs], (uint32_t)((it >> 1) & 1));
-        mbar_wait_relaxed(&kv_full[ks], (uint32_t)((step / kKvStages) & 1));
+        mbar_wait_relaxed(&kv_full[ks], (uint32_t)((t / kKvStages) & 1));
         tc_fence_after();
         const uint32_t n = (uint32_t)(j == nb - 1 ? bl : bn);
         const uint32_t idesc = make_idesc_bf16(128, n, 0, 0);
@@ -250,36 +258,59 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
                     make_smem_desc(ak + k * 32, 16, kSbo, kLayout), idesc, k > 0 ? 1u : 0u);
         umma_commit(&s_full[X]);
       };
+      auto item_blocks = [&](int it, int (&nbx)[2]) {
+        int b, h, q0;
+        decode((int)blockIdx.x + it * (int)gridDim.x, b, h, q0);
+        nbx[0] = tile_blocks(q0, 0);
+        nbx[1] = tile_blocks(q0, 1);
+      };
 
-      if (nsteps > 0) {
-        issue_qk(0, 0);
-        if (has_tile(0, 1)) issue_qk(0, 1);
+      // Per tile the stream is S(0), [P.V(j), S(j+1)] ...; the two tiles alternate, so one tile's softmax overlaps the
+      // other's products, and the first scores of the next item are issued behind the last P.V of this one.
+      int nbx[2] = {0, 0}, nnx[2] = {0, 0};
+      int t = 0;                                                 // K/V ring step of (it, j)
+      if (my_items > 0) {
+        item_blocks(0, nbx);
+        issue_qk(0, 0, 0, 0);
+        if (nbx[1] > 0) issue_qk(0, 0, 1, 0);
       }
-      for (int step = 0; step < nsteps; ++step) {
-        const int it = step / nb, j = step - it * nb;
-        const int qs = it & 1, ks = step % kKvStages;
-        const bool hb = has_tile(step, 1);
-        const int nks = (j == nb - 1 ? bl : bn) >> 4;
-        const uint32_t av = sKV + ks * Cfg::kKvStage + Cfg::kKvHalf;
-        for (int X = 0; X < 2; ++X) {
-          if (X == 1 && !hb) break;
-          mbar_wait(&p_ready[X], cnt[X] & 1u);
-          ++cnt[X];
-          tc_fence_after();
-          const uint32_t t_s = tmem_base + (uint32_t)(X * Cfg::kSW), t_o = tmem_base + (uint32_t)(2 * Cfg::kSW + X * D);
-          for (int kk = 0; kk < nks; ++kk)
-            umma_bf16_ts(t_o, t_s + 32u * (kk >> 1) + 8u * (kk & 1),
-                         make_smem_desc(av + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc_pv,
-                         (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&pv_done[X]);
-          if (X == 1 || !hb) {   // every MMA that reads this K/V stage (and, on the last block, the Q stage) is issued
-            umma_commit(&kv_empty[ks]);
-            if (j == nb - 1) umma_commit(&q_empty[qs]);
+      for (int it = 0; it < my_items; ++it) {
+        const int qs = it & 1;
+        const int nst = max(nbx[0], nbx[1]);
+        const bool has_next = it + 1 < my_items;
+        if (has_next) item_blocks(it + 1, nnx);
+        for (int j = 0; j < nst; ++j, ++t) {
+          const int ks = t % kKvStages;
+          const int nks = (j == nb - 1 ? bl : bn) >> 4;
+          const uint32_t av = sKV + ks * Cfg::kKvStage + Cfg::kKvHalf;
+          const bool last = j + 1 == nst;
+          const int lastX = (j < nbx[1]) ? 1 : 0;                // the last tile that reads this K/V stage
+          for (int X = 0; X < 2; ++X) {
+            if (j < nbx[X]) {
+              mbar_wait(&p_ready[X], cnt[X] & 1u);
+              ++cnt[X];
+              tc_fence_after();
+              const uint32_t t_s = tmem_base + (uint32_t)(X * Cfg::kSW), t_o = tmem_base + (uint32_t)(2 * Cfg::kSW + X * D);
+              for (int kk = 0; kk < nks; ++kk)
+                umma_bf16_ts(t_o, t_s + 32u * (kk >> 1) + 8u * (kk & 1),
+                             make_smem_desc(av + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc_pv,
+                             (j > 0 || kk > 0) ? 1u : 0u);
+              umma_commit(&pv_done[X]);
+            }
+            if (X == lastX) {      // every MMA that reads this K/V stage (and, on the last block, the Q stage) is issued
+              umma_commit(&kv_empty[ks]);
+              if (last) umma_commit(&q_empty[qs]);
+            }
+            // the next scores of this tile: the next key block, or the first block of the next item
+            if (!last) {
+              if (j + 1 < nbx[X]) issue_qk(it, j + 1, X, t + 1);
+            } else if (has_next && nnx[X] > 0) {
+              issue_qk(it + 1, 0, X, t + 1);
+            }
           }
-          if (step + 1 < nsteps && has_tile(step + 1, X)) issue_qk(step + 1, X);
         }
-        // tile B absent in this step but present in the next one: its first scores were not issued above
-        if (!hb && step + 1 < nsteps && has_tile(step + 1, 1)) issue_qk(step + 1, 1);
+        nbx[0] = nnx[0];
+        nbx[1] = nnx[1];
       }
     }
     __syncwarp();
@@ -317,7 +348,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
       int b, h, q0;
       decode(item, b, h, q0);
       const int r0 = q0 + X * 128;
-      if (r0 >= p.Sq) continue;                       // tile B of a short item: nothing was issued for it
+      const int nbt = tile_blocks(q0, X);             // key blocks of this tile (fewer under the causal mask)
+      if (nbt == 0) continue;                         // tile B of a short item: nothing was issued for it
       const bool active = r0 + wq * 32 < p.Sq;        // warp-uniform: a warp whose 32 rows are all out of range idles
       const int i = r0 + row;
       const long long bh = (long long)b * p.nh + h;
@@ -341,7 +373,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
 
       float m_run = -INFINITY, l = 0.f;
       const unsigned long long prow = (unsigned long long)bh * p.Sq + i;
-      for (int j = 0; j < nb; ++j) {
+      for (int j = 0; j < nbt; ++j) {
         const int width = (j == nb - 1) ? bl : bn;
         const int nch = (width + 31) >> 5;
         const int nblk = (nch + 1) >> 1;   // 64-column blocks: one set of Philox calls each

@@ -1,5 +1,6 @@
-"""Micro-benchmark of the attention kernels: attn_bench.py [B] [dropout 0/1] [heads] [d_head] [S]
-(default-model shape B=256, 8 heads, d=32, S=200; scaled config: 16 1 16 64 1000)."""
+"""Micro-benchmark of the attention kernels: attn_bench.py [B] [dropout 0/1] [heads] [d_head] [S] [mask mode]
+(default-model shape B=256, 8 heads, d=32, S=200; scaled config: 16 1 16 64 1000; mask mode 1 = encoder mask
+eye | key_valid (default), 2 = causal: FLOPs are still counted for the full S x S product)."""
 import sys
 import torch
 sys.path.insert(0, '.')
@@ -10,6 +11,7 @@ drop_on = (sys.argv[2] != "0") if len(sys.argv) > 2 else True
 nh = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 d = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 S = int(sys.argv[5]) if len(sys.argv) > 5 else 200
+mask_mode = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 H = nh * d
 dev = "cuda"
 qkv = torch.randn(B * S, 3 * H, device=dev).to(torch.bfloat16)
@@ -25,7 +27,7 @@ do = ops.DropSpec(seed, 2, 0.4) if drop_on else ops.NO_DROP
 d_o = torch.randn(B * S, H, device=dev).to(torch.bfloat16)
 dqkv = torch.zeros(B * S, 3 * H, device=dev, dtype=torch.bfloat16)
 delta = torch.zeros(B, nh, S, device=dev)
-kw = dict(B=B, n_heads=nh, Sq=S, Sk=S, d_head=d, mask_mode=1, drop_p=dp, drop_o=do, p_keep=p_keep)
+kw = dict(B=B, n_heads=nh, Sq=S, Sk=S, d_head=d, mask_mode=mask_mode, drop_p=dp, drop_o=do, p_keep=p_keep)
 
 
 def timeit(name, fn, flops, iters=20):
