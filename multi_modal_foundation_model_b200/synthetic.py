@@ -55,6 +55,17 @@ def make_batch(batch: int, n_neurons: int, n_behaviors: int = 2, n_bins: int = 1
     return out
 
 
+_MOD_INDEX: Dict[tuple, torch.Tensor] = {}
+
+
+def _modality_index(idx: int, device) -> torch.Tensor:
+    key = (str(device), idx)
+    t = _MOD_INDEX.get(key)
+    if t is None:
+        t = _MOD_INDEX[key] = torch.tensor(idx, device=device)
+    return t
+
+
 def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[str], device="cpu",
                   extra_behaviors: int = 0, compact_masks: bool = False) -> Dict[str, Dict[str, object]]:
     """Build ``mod_dict`` exactly as the trainer does (``trainer/base.py:51-103``) for multi-modal
@@ -62,7 +73,8 @@ def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[s
     ``token_masking`` (eval_mask None -> Masker samples) or ``None`` (single-modality output).
 
     ``compact_masks`` replaces the trainer's dense (B,T,N) int64 all-ones / all-zeros ``eval_mask`` tensors (137 MB each
-    at B=256, N=668; only column 0 is ever read, mm.py:270) by the scalars 1 / 0 the B200 path also accepts."""
+    at B=256, N=668; only column 0 is ever read, mm.py:270) by the scalars 1 / 0 the B200 path also accepts, and the
+    per-step blocking copies of the modality indices by cached device scalars (no host synchronisation in the step)."""
     spikes = batch["spikes_data"].to(device, non_blocking=True)
     target = batch["target"].to(device, non_blocking=True)
     attn = batch["time_attn_mask"].to(device, non_blocking=True)
@@ -70,8 +82,14 @@ def make_mod_dict(batch: Dict[str, object], avail_mod, training_mode: Optional[s
     mod_dict: Dict[str, Dict[str, object]] = {}
     for idx, mod in enumerate(avail_mod):
         d: Dict[str, object] = {}
-        d["inputs_modality"] = torch.tensor(idx, device=device)
-        d["targets_modality"] = torch.tensor(idx, device=device)
+        if compact_masks:
+            # the trainer's `torch.tensor(idx).to(device)` (trainer/base.py:60-61) is a blocking copy from pageable memory:
+            # four stream synchronisations per step, each of which drains the launch queue (tools/e2e_probe.py: host
+            # enqueue time = device time, +0.25 ms per step).  The wire-format dict keeps one device scalar per index.
+            d["inputs_modality"] = d["targets_modality"] = _modality_index(idx, device)
+        else:
+            d["inputs_modality"] = torch.tensor(idx, device=device)
+            d["targets_modality"] = torch.tensor(idx, device=device)
         d["inputs_attn_mask"] = attn
         d["inputs_timestamp"] = ts
         d["targets_timestamp"] = ts
