@@ -489,7 +489,7 @@ def main():
         host_batches = [dict(hb, spikes_data=hb["spikes_data"].to(torch.uint8).pin_memory()) for hb in fp32_batches]
         pf._next = None
         e2e_compact[0] = True          # the wire format of this path: byte counts + compact masks
-        for i in range(6 if not wl.multi else NB):
+        for i in range(6 if not wl.multi else 3 * NB):   # (multi-session: every session's byte-input plan built, run, captured)
             step_e2e(i)
         ms_e2e_u8 = timed(step_e2e, a.steps)
         e2e_compact[0] = False
