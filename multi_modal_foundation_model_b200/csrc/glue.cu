@@ -28,49 +28,62 @@ MMFM_DEVINL float block_sum(float v, float* sh) {  // sh: >= 32 floats
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// mask preparation (single CTA; B*S elements)
+// mask preparation (B*S elements).  grid = (slices, modalities): the step's first kernel sits on the critical path of
+// everything else, and as a single CTA it spent 44 us on 25 dependent rounds of strided int64 loads.  Every CTA adds its
+// masked-token count to a per-modality counter; the last one to finish (ticket) turns the counters into n_examples /
+// inv_n and leaves counters and ticket at zero for the next launch.  Counts are integers: the result does not depend on
+// the arrival order.  (One mask_prep in flight per device at a time: the engine issues it on its single stream.)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) mask_prep_kernel(const mmfm_mask_args a, unsigned char* __restrict__ zero_flags,
-                                                          unsigned char* __restrict__ key_valid,
-                                                          unsigned char* __restrict__ tok_mask,
-                                                          long long* __restrict__ n_examples,
-                                                          float* __restrict__ inv_n) {
+__device__ unsigned int g_mp_count[MMFM_MAX_MOD];
+__device__ unsigned int g_mp_ticket;
+
+__global__ void __launch_bounds__(256) mask_prep_kernel(const mmfm_mask_args a, unsigned char* __restrict__ zero_flags,
+                                                         unsigned char* __restrict__ key_valid,
+                                                         unsigned char* __restrict__ tok_mask,
+                                                         long long* __restrict__ n_examples,
+                                                         float* __restrict__ inv_n) {
   __shared__ float sh[32];
-  __shared__ long long total;
   const int S = a.n_mod * a.T;
-  if (threadIdx.x == 0) total = 0;
-  for (int m = 0; m < a.n_mod; ++m) {
-    int cnt = 0;
-    const uint32_t thresh = a.sample_thresh ? a.sample_thresh[m] : 0u;
-    const unsigned long long seed = (thresh && a.seed) ? *a.seed : 0ull;
-    for (int e = threadIdx.x; e < a.B * a.T; e += blockDim.x) {
-      const int b = e / a.T, t = e - b * a.T;
-      const long long at = a.attn[m][(long long)b * a.attn_sb[m] + (long long)t * a.attn_st[m]];
-      long long mk;
-      if (thresh) {   // device-side Bernoulli(ratio) field (Masker temporal mode, models/masker.py:85-86,132)
-        const uint4 w = philox4x32((uint32_t)(e >> 2), 0u, MMFM_MASK_SITE + (uint32_t)m, 2u, (uint32_t)seed,
-                                   (uint32_t)(seed >> 32));
-        const uint32_t word = (e & 3) == 0 ? w.x : (e & 3) == 1 ? w.y : (e & 3) == 2 ? w.z : w.w;
-        mk = word < thresh;
-      } else {
-        mk = a.mask[m] ? a.mask[m][(long long)b * a.mask_sb[m] + (long long)t * a.mask_st[m]] : 0;
-      }
-      mk &= at;  // mm.py:270
-      const long long o = (long long)b * S + m * a.T + t;
-      key_valid[o] = at != 0;
-      tok_mask[o] = (unsigned char)(mk != 0);
-      if (b == 0) zero_flags[m * a.T + t] = (mk == 1);
-      cnt += (int)mk;  // mask entries are 0/1 (mm.py:231 sums the expanded mask)
+  const int m = blockIdx.y;
+  int cnt = 0;
+  const uint32_t thresh = a.sample_thresh ? a.sample_thresh[m] : 0u;
+  const unsigned long long seed = (thresh && a.seed) ? *a.seed : 0ull;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.B * a.T; e += gridDim.x * blockDim.x) {
+    const int b = e / a.T, t = e - b * a.T;
+    const long long at = a.attn[m][(long long)b * a.attn_sb[m] + (long long)t * a.attn_st[m]];
+    long long mk;
+    if (thresh) {   // device-side Bernoulli(ratio) field (Masker temporal mode, models/masker.py:85-86,132)
+      const uint4 w = philox4x32((uint32_t)(e >> 2), 0u, MMFM_MASK_SITE + (uint32_t)m, 2u, (uint32_t)seed,
+                                 (uint32_t)(seed >> 32));
+      const uint32_t word = (e & 3) == 0 ? w.x : (e & 3) == 1 ? w.y : (e & 3) == 2 ? w.z : w.w;
+      mk = word < thresh;
+    } else {
+      mk = a.mask[m] ? a.mask[m][(long long)b * a.mask_sb[m] + (long long)t * a.mask_st[m]] : 0;
     }
-    const float c = block_sum((float)cnt, sh);  // exact: counts < 2^24
-    if (threadIdx.x == 0) {
-      const long long n = (long long)(c + 0.5f) * a.channels[m];
-      n_examples[m] = n;
-      total += n;
+    mk &= at;  // mm.py:270
+    const long long o = (long long)b * S + m * a.T + t;
+    key_valid[o] = at != 0;
+    tok_mask[o] = (unsigned char)(mk != 0);
+    if (b == 0) zero_flags[m * a.T + t] = (mk == 1);
+    cnt += (int)mk;  // mask entries are 0/1 (mm.py:231 sums the expanded mask)
+  }
+  const float c = block_sum((float)cnt, sh);  // exact: counts < 2^24
+  if (threadIdx.x == 0) {
+    atomicAdd(&g_mp_count[m], (unsigned int)(c + 0.5f));
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&g_mp_ticket, 1u);
+    if (ticket == gridDim.x * gridDim.y - 1) {   // every other CTA's count is in
+      __threadfence();
+      long long total = 0;
+      for (int mm = 0; mm < a.n_mod; ++mm) {
+        const long long n = (long long)atomicExch(&g_mp_count[mm], 0u) * a.channels[mm];
+        n_examples[mm] = n;
+        total += n;
+      }
+      inv_n[0] = 1.0f / (float)total;  // total == 0 -> inf (reference: NaN loss)
+      g_mp_ticket = 0u;
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) inv_n[0] = 1.0f / (float)total;  // total == 0 -> inf (reference: NaN loss)
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -895,7 +908,9 @@ extern "C" int mmfm_mask_prep(const mmfm_mask_args* a, unsigned char* zero_flags
     MMFM_REQUIRE(a->attn[m] != nullptr, "mmfm_mask_prep: modality %d has no attention mask", m);
     MMFM_REQUIRE(a->channels[m] > 0, "mmfm_mask_prep: modality %d has no channels", m);
   }
-  mask_prep_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*a, zero_flags, key_valid, tok_mask, n_examples, inv_n);
+  int slices = (a->B * a->T + 255) / 256;
+  if (slices > 64) slices = 64;
+  mask_prep_kernel<<<dim3(slices, a->n_mod), 256, 0, (cudaStream_t)stream>>>(*a, zero_flags, key_valid, tok_mask, n_examples, inv_n);
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
