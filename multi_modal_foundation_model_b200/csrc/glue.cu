@@ -125,25 +125,42 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const flo
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), accm = acc;
   long long cur = -1;
   if (sl < kAsmLanes) {
-    for (int b = b0 + sl; b < b1; b += kAsmLanes) {
-      const long long row = ((long long)b * S + off + t) * H;
-      float4 v = __ldg(reinterpret_cast<const float4*>(g + row) + c);
-      if (g2) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(g2 + row) + c);
-        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-      }
-      accm.x += v.x; accm.y += v.y; accm.z += v.z; accm.w += v.w;
-      if (dpos) {
-        const long long idx = ts[(long long)b * T + t];
-        if (idx != cur) {
-          if (cur >= 0) {
-            float* d = dpos + cur * H + c * 4;
-            atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    // four samples per round: all their row loads are issued before the first use (same summation order)
+    constexpr int kU = 4;
+    for (int bb = b0 + sl; bb < b1; bb += kAsmLanes * kU) {
+      float4 v[kU];
+      long long id[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int b = bb + u * kAsmLanes;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        id[u] = -1;
+        if (b < b1) {
+          const long long row = ((long long)b * S + off + t) * H;
+          v[u] = __ldg(reinterpret_cast<const float4*>(g + row) + c);
+          if (g2) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(g2 + row) + c);
+            v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
           }
-          cur = idx;
-          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (dpos) id[u] = ts[(long long)b * T + t];
         }
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (bb + u * kAsmLanes >= b1) break;
+        accm.x += v[u].x; accm.y += v[u].y; accm.z += v[u].z; accm.w += v[u].w;
+        if (dpos) {
+          const long long idx = id[u];
+          if (idx != cur) {
+            if (cur >= 0) {
+              float* d = dpos + cur * H + c * 4;
+              atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+            }
+            cur = idx;
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
       }
     }
     if (dpos && cur >= 0) {
