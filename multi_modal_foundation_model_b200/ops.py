@@ -169,7 +169,8 @@ def cast_bf16(x: torch.Tensor, y: Optional[torch.Tensor], yt: Optional[torch.Ten
     R = R if R is not None else x.shape[0]
     Cc = Cc if Cc is not None else x.shape[1]
     _launch("mmfm_cast_bf16", x.data_ptr(), ldx if ldx is not None else x.stride(0), _p(y),
-            y.stride(0) if y is not None else 0, _p(yt), yt.stride(0) if yt is not None else 0, R, Cc)
+            y.stride(0) if y is not None else 0, _p(yt), yt.stride(0) if yt is not None else 0, R, Cc,
+            meta={"bytes": float(R) * Cc * (4 + 2 * (y is not None) + 2 * (yt is not None))})
 
 
 def cast_bf16_multi(items_dev: torch.Tensor, n_items: int, total_tiles: int) -> None:
@@ -302,17 +303,19 @@ def mask_prep(masks: Sequence[Optional[torch.Tensor]], attns: Sequence[torch.Ten
 
 
 def embed_assemble(mod_row, pos, ts, emb, *, B, T, S, off, H) -> None:
-    _launch("mmfm_embed_assemble", mod_row.data_ptr(), _p(pos), _p(ts), emb.data_ptr(), B, T, S, off, H)
+    _launch("mmfm_embed_assemble", mod_row.data_ptr(), _p(pos), _p(ts), emb.data_ptr(), B, T, S, off, H,
+            meta={"bytes": 4.0 * B * T * H})                       # emb rows written (the tables stay in cache)
 
 
 def embed_assemble_bwd(g, g2, ts, dpos, dmod, *, B, T, S, off, H) -> None:
-    _launch("mmfm_embed_assemble_bwd", g.data_ptr(), _p(g2), _p(ts), _p(dpos), dmod.data_ptr(), B, T, S, off, H)
+    _launch("mmfm_embed_assemble_bwd", g.data_ptr(), _p(g2), _p(ts), _p(dpos), dmod.data_ptr(), B, T, S, off, H,
+            meta={"bytes": 4.0 * B * T * H * (2 if g2 is not None else 1)})   # gradient rows read
 
 
 def embed_grad_prep(dx, dtok, row_zero, drop: DropSpec, *, B, T, S, off, H) -> None:
     d = drop.c()
     _launch("mmfm_embed_grad_prep", dx.data_ptr(), dtok.data_ptr(), _p(row_zero), C.byref(d), B, T, S, off, H,
-            keep=(d,))
+            keep=(d,), meta={"bytes": 6.0 * B * T * H})            # fp32 rows in, bf16 rows out
 
 
 def smallc_embed_fwd(inp, W1, b1, W2, b2, emb, x, hid, row_zero, drop: DropSpec, act_scale, act, *, B, T, S, off, Cc,
@@ -320,7 +323,7 @@ def smallc_embed_fwd(inp, W1, b1, W2, b2, emb, x, hid, row_zero, drop: DropSpec,
     d = drop.c()
     _launch("mmfm_smallc_embed_fwd", inp.data_ptr(), W1.data_ptr(), _p(b1), W2.data_ptr(), _p(b2), emb.data_ptr(),
             x.data_ptr(), hid.data_ptr(), _p(row_zero), C.byref(d), float(act_scale), act, B, T, S, off, Cc, H,
-            keep=(d,))
+            keep=(d,), meta={"bytes": float(B) * T * (8.0 * H + 4.0 * Cc + 8.0 * Cc)})   # emb rows in, x rows out
 
 
 def smallc_embed_bwd(inp, hid, W2, dx, row_zero, drop: DropSpec, act_scale, act, dW1, db1, dW2, db2, *, B, T, S, off,
@@ -328,16 +331,17 @@ def smallc_embed_bwd(inp, hid, W2, dx, row_zero, drop: DropSpec, act_scale, act,
     d = drop.c()
     _launch("mmfm_smallc_embed_bwd", inp.data_ptr(), hid.data_ptr(), W2.data_ptr(), dx.data_ptr(), _p(row_zero),
             C.byref(d), float(act_scale), act, dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(), db2.data_ptr(), B, T, S,
-            off, Cc, H, keep=(d,))
+            off, Cc, H, keep=(d,), meta={"bytes": float(B) * T * (4.0 * H + 12.0 * Cc)})   # dx rows in
 
 
 def smallc_head_fwd(y, W, b, preds, *, R, H, Cc) -> None:
-    _launch("mmfm_smallc_head_fwd", y.data_ptr(), W.data_ptr(), _p(b), preds.data_ptr(), R, H, Cc)
+    _launch("mmfm_smallc_head_fwd", y.data_ptr(), W.data_ptr(), _p(b), preds.data_ptr(), R, H, Cc,
+            meta={"bytes": float(R) * (2.0 * H + 4.0 * Cc)})
 
 
 def smallc_head_bwd(y, W, dpreds, dy, dW, db, *, R, H, Cc) -> None:
     _launch("mmfm_smallc_head_bwd", y.data_ptr(), W.data_ptr(), dpreds.data_ptr(), dpreds.stride(0), dy.data_ptr(),
-            dW.data_ptr(), db.data_ptr(), R, H, Cc)
+            dW.data_ptr(), db.data_ptr(), R, H, Cc, meta={"bytes": float(R) * (4.0 * H + 2.0 * Cc)})
 
 
 def loss_fwd_bwd(preds, targets, tok_mask, inv_n, kind, partials, dpreds, *, B, T, Cc, S, off) -> None:
