@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMFM_ABI_VERSION 3
+#define MMFM_ABI_VERSION 4
 
 const char* mmfm_last_error(void);
 int mmfm_abi_version(void);
@@ -108,6 +108,31 @@ int mmfm_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
 int mmfm_layernorm_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                        const float* dres, float* dx, void* dxb, const mmfm_dropout* drop, float* dgamma,
                        float* dbeta, int R, int H, int modmajor_T, int S, void* stream);
+
+/* ---- Several LayerNorms over ONE input: the `context_norm` of every decoder layer normalises the same encoder context
+ *      (decoder_embeddings.py:141-145 inside the layer loop of :133-147), so x-hat, mean and rstd are shared and only
+ *      the affine pairs differ.  Forward: x is read once, n bf16 outputs are written, mean / rstd are saved once.
+ *      Backward: dx = LN'(sum_l dy_l . gamma_l) -- LN' is linear in its upstream gradient, so one normalisation of the
+ *      gamma-weighted sum replaces n backward passes over x and n read-modify-writes of dx -- with the optional bf16
+ *      copy dxb; dgamma[l] / dbeta[l] += column sums of dy_l . x-hat / dy_l.  H in {128, 256, 512}, n <= MMFM_MAX_LN. */
+#define MMFM_MAX_LN 8
+typedef struct {
+  const float* x;                      /* [R, H] fp32 */
+  int R, H, n;
+  float eps;
+  const float* gamma[MMFM_MAX_LN];
+  const float* beta[MMFM_MAX_LN];      /* forward only */
+  void* y[MMFM_MAX_LN];                /* forward: bf16 [R, H] outputs */
+  float* mean;                         /* [R] saved by the forward, read by the backward */
+  float* rstd;
+  const void* dy[MMFM_MAX_LN];         /* backward: bf16 [R, H] upstream gradients */
+  float* dgamma[MMFM_MAX_LN];
+  float* dbeta[MMFM_MAX_LN];
+  float* dx;                           /* backward: fp32 [R, H] (written, not accumulated) */
+  void* dxb;                           /* backward: optional bf16 copy of dx */
+} mmfm_ln_multi_args;
+int mmfm_layernorm_fwd_multi(const mmfm_ln_multi_args* a, void* stream);
+int mmfm_layernorm_bwd_multi(const mmfm_ln_multi_args* a, void* stream);
 
 /* ---- ScaleNorm (mm_utils.py:31-39, config `use_scalenorm: true`): y(bf16) = x * g[0] / max(||x||_2, eps); the
  *      reciprocal norms are saved in rnorm[R].  Backward: dx = dres + g*rnorm*(dy - xhat <dy,xhat>), optional

@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xptxas", "-v"]
 
 MAX_MOD = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 MASK_SITE = 8192
 
 
@@ -127,6 +127,19 @@ class MaskArgs(C.Structure):
     ]
 
 
+MAX_LN = 8
+
+
+class LnMultiArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("R", C.c_int), ("H", C.c_int), ("n", C.c_int), ("eps", C.c_float),
+        ("gamma", C.c_void_p * MAX_LN), ("beta", C.c_void_p * MAX_LN), ("y", C.c_void_p * MAX_LN),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("dy", C.c_void_p * MAX_LN), ("dgamma", C.c_void_p * MAX_LN), ("dbeta", C.c_void_p * MAX_LN),
+        ("dx", C.c_void_p), ("dxb", C.c_void_p),
+    ]
+
+
 class CastItem(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("ld_src", C.c_longlong),
@@ -158,6 +171,8 @@ SIGNATURES = {
     "mmfm_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _ll, _vp],
     "mmfm_layernorm_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "mmfm_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _DP, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mmfm_layernorm_fwd_multi": [C.POINTER(LnMultiArgs), _vp],
+    "mmfm_layernorm_bwd_multi": [C.POINTER(LnMultiArgs), _vp],
     "mmfm_scalenorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "mmfm_scalenorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _DP, _vp, _i, _i, _f, _vp],
     "mmfm_attention_fwd": [C.POINTER(AttnArgs), _vp],

@@ -250,6 +250,160 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Several LayerNorms over one input (the decoder layers' context_norm, decoder_embeddings.py:141-145): see the header.
+// Warp = row as above; H = 128 * NV.
+// ------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_fwd_multi_kernel(const mmfm_ln_multi_args a) {
+  pdl_enter();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = a.R, H = a.H;
+  const float invH = 1.0f / (float)H;
+  constexpr int U = 2;   // rows per warp in flight
+  for (long long r0 = ((long long)blockIdx.x * kLnWarps + warp) * U; r0 < R; r0 += (long long)gridDim.x * kLnWarps * U) {
+    float4 v[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        v[u][j] = (r0 + u < R) ? __ldg(reinterpret_cast<const float4*>(a.x + (r0 + u) * H) + lane + 32 * j)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) s += (v[u][j].x + v[u][j].y) + (v[u][j].z + v[u][j].w);
+      const float mu = warp_sum(s) * invH;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        v[u][j].x -= mu; v[u][j].y -= mu; v[u][j].z -= mu; v[u][j].w -= mu;
+        q += (v[u][j].x * v[u][j].x + v[u][j].y * v[u][j].y) + (v[u][j].z * v[u][j].z + v[u][j].w * v[u][j].w);
+      }
+      const float rs = rsqrtf(warp_sum(q) * invH + a.eps);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) { v[u][j].x *= rs; v[u][j].y *= rs; v[u][j].z *= rs; v[u][j].w *= rs; }   // x-hat
+      if (lane == 0 && r0 + u < R) {
+        a.mean[r0 + u] = mu;
+        a.rstd[r0 + u] = rs;
+      }
+    }
+    for (int l = 0; l < a.n; ++l) {
+      float4 gm[NV], bt[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        gm[j] = __ldg(reinterpret_cast<const float4*>(a.gamma[l]) + lane + 32 * j);
+        bt[j] = __ldg(reinterpret_cast<const float4*>(a.beta[l]) + lane + 32 * j);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r0 + u >= R) break;
+        bf16* yr = reinterpret_cast<bf16*>(a.y[l]) + (r0 + u) * H;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          uint2 o;
+          o.x = pack_bf16x2(fmaf(v[u][j].x, gm[j].x, bt[j].x), fmaf(v[u][j].y, gm[j].y, bt[j].y));
+          o.y = pack_bf16x2(fmaf(v[u][j].z, gm[j].z, bt[j].z), fmaf(v[u][j].w, gm[j].w, bt[j].w));
+          reinterpret_cast<uint2*>(yr)[lane + 32 * j] = o;
+        }
+      }
+    }
+  }
+}
+
+template <int NV, int NL>
+__global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_multi_kernel(const mmfm_ln_multi_args a) {
+  pdl_enter();
+  __shared__ float red[kLnWarps][128 * NV + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = a.R, H = a.H;
+  const float invH = 1.0f / (float)H;
+  float4 accg[NL][NV], accb[NL][NV];
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      accg[l][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      accb[l][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
+    const float mu = __ldg(a.mean + r), rs = __ldg(a.rstd + r);
+    uint2 dv[NL][NV];
+#pragma unroll
+    for (int l = 0; l < NL; ++l)      // every layer's gradient row in flight together with x
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        dv[l][j] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(a.dy[l]) + r * H) + lane + 32 * j);
+    float4 xh[NV], gd[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + r * H) + lane + 32 * j);
+      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      gd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[l]) + lane + 32 * j);
+        const float2 d01 = unpack_bf16x2(dv[l][j].x), d23 = unpack_bf16x2(dv[l][j].y);
+        accb[l][j].x += d01.x; accb[l][j].y += d01.y; accb[l][j].z += d23.x; accb[l][j].w += d23.y;
+        accg[l][j].x = fmaf(d01.x, xh[j].x, accg[l][j].x); accg[l][j].y = fmaf(d01.y, xh[j].y, accg[l][j].y);
+        accg[l][j].z = fmaf(d23.x, xh[j].z, accg[l][j].z); accg[l][j].w = fmaf(d23.y, xh[j].w, accg[l][j].w);
+        gd[j].x = fmaf(d01.x, gm.x, gd[j].x); gd[j].y = fmaf(d01.y, gm.y, gd[j].y);
+        gd[j].z = fmaf(d23.x, gm.z, gd[j].z); gd[j].w = fmaf(d23.y, gm.w, gd[j].w);
+      }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      s1 += (gd[j].x + gd[j].y) + (gd[j].z + gd[j].w);
+      s2 += (gd[j].x * xh[j].x + gd[j].y * xh[j].y) + (gd[j].z * xh[j].z + gd[j].w * xh[j].w);
+    }
+    const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 o;
+      o.x = rs * (gd[j].x - m1 - xh[j].x * m2);
+      o.y = rs * (gd[j].y - m1 - xh[j].y * m2);
+      o.z = rs * (gd[j].z - m1 - xh[j].z * m2);
+      o.w = rs * (gd[j].w - m1 - xh[j].w * m2);
+      reinterpret_cast<float4*>(a.dx + r * H)[lane + 32 * j] = o;
+      if (a.dxb) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.dxb) + r * H)[lane + 32 * j] = pk;
+      }
+    }
+  }
+  // CTA reduction of the column partials, then one atomic per column per CTA and layer
+#pragma unroll 1
+  for (int pass = 0; pass < 2 * NL; ++pass) {
+    if (pass > 0) __syncthreads();
+    const int l = pass >> 1;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ll = 0; ll < NL; ++ll)
+        if (ll == l) v = (pass & 1) ? accb[ll][j] : accg[ll][j];
+      float* dst = &red[warp][(lane + 32 * j) * 4];
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    float* out = (pass & 1) ? a.dbeta[l] : a.dgamma[l];
+    if (out) {
+      for (int c = threadIdx.x; c < H; c += kLnWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+        atomicAdd(out + c, s);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // ScaleNorm (mm_utils.py:31-39, `use_scalenorm: true`): y = x * g / max(||x||_2, eps), g a scalar parameter.
 // Warp per row, any H % 4 == 0 (the row is re-read through L1 for the second pass).  Off the default config's path
 // (mm.yaml:41 ships use_scalenorm: false), so these are plain bandwidth kernels without the register-path variants.
@@ -430,6 +584,69 @@ extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* m
 #undef LN_BWD
   MMFM_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int ln_multi_check(const mmfm_ln_multi_args* a, const char* who, bool bwd) {
+  MMFM_REQUIRE(a != nullptr, "%s: null args", who);
+  MMFM_REQUIRE(a->x && a->mean && a->rstd, "%s: null pointer", who);
+  MMFM_REQUIRE(a->n >= 1 && a->n <= MMFM_MAX_LN, "%s: n=%d outside [1,%d]", who, a->n, MMFM_MAX_LN);
+  MMFM_REQUIRE(a->R > 0 && (a->H == 128 || a->H == 256 || a->H == 512), "%s: bad shape R=%d H=%d (H in {128, 256, 512})", who,
+               a->R, a->H);
+  // the backward keeps 2 * n * (H / 128) float4 column partials in registers
+  MMFM_REQUIRE((a->H / 128) * a->n <= 12, "%s: n=%d LayerNorms of width %d exceed the register budget (n * H / 128 <= 12)", who,
+               a->n, a->H);
+  for (int l = 0; l < a->n; ++l) {
+    MMFM_REQUIRE(a->gamma[l] != nullptr, "%s: layer %d has no gamma", who, l);
+    if (bwd) MMFM_REQUIRE(a->dy[l] != nullptr, "%s: layer %d has no upstream gradient", who, l);
+    else MMFM_REQUIRE(a->beta[l] && a->y[l], "%s: layer %d has no beta / output", who, l);
+  }
+  if (bwd) MMFM_REQUIRE(a->dx != nullptr, "%s: null dx", who);
+  return 0;
+}
+
+extern "C" int mmfm_layernorm_fwd_multi(const mmfm_ln_multi_args* a, void* stream) {
+  if (int rc = ln_multi_check(a, "mmfm_layernorm_fwd_multi", false)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid_fwd(a->R, a->H);
+  switch (a->H) {
+    case 128: MMFM_CHECK_CUDA(launch_pdl(layernorm_fwd_multi_kernel<1>, dim3(grid), dim3(kLnWarps * 32), 0, st, *a)); break;
+    case 256: MMFM_CHECK_CUDA(launch_pdl(layernorm_fwd_multi_kernel<2>, dim3(grid), dim3(kLnWarps * 32), 0, st, *a)); break;
+    default: MMFM_CHECK_CUDA(launch_pdl(layernorm_fwd_multi_kernel<4>, dim3(grid), dim3(kLnWarps * 32), 0, st, *a)); break;
+  }
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NV>
+static int ln_bwd_multi_launch(const mmfm_ln_multi_args* a, cudaStream_t st) {
+  // one resident wave: the register-heavy kernel (2 * n * NV float4 accumulators) fits one or two CTAs per SM
+  int grid = device_sm_count() * (NV * a->n <= 4 ? 2 : 1);
+  const int max_grid = (a->R + kLnWarps - 1) / kLnWarps;
+  if (grid > max_grid) grid = max_grid;
+#define LNB(NL) MMFM_CHECK_CUDA(launch_pdl(layernorm_bwd_multi_kernel<NV, NL>, dim3(grid), dim3(kLnWarps * 32), 0, st, *a))
+  switch (a->n) {
+    case 1: LNB(1); break;
+    case 2: LNB(2); break;
+    case 3: LNB(3); break;
+    case 4: LNB(4); break;
+    case 5: LNB(5); break;
+    case 6: LNB(6); break;
+    case 7: LNB(7); break;
+    default: LNB(8); break;
+  }
+#undef LNB
+  MMFM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmfm_layernorm_bwd_multi(const mmfm_ln_multi_args* a, void* stream) {
+  if (int rc = ln_multi_check(a, "mmfm_layernorm_bwd_multi", true)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->H) {
+    case 128: return ln_bwd_multi_launch<1>(a, st);
+    case 256: return ln_bwd_multi_launch<2>(a, st);
+    default: return ln_bwd_multi_launch<4>(a, st);
+  }
 }
 
 extern "C" int mmfm_scalenorm_fwd(const float* x, const float* g, void* y, float* rnorm, int R, int H, float eps,

@@ -15,6 +15,7 @@ There is no PyTorch fallback: every arithmetic step is a kernel of libmmfm_b200.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -66,6 +67,22 @@ def embedding_groups(model):
 def live_stores():
     """Flat parameter stores of the engines alive in this process (optim.AdamW finds its parameters' owner here)."""
     return list(_STORES)
+
+
+def fuse_context_norms(named, n_dec: int) -> bool:
+    """The `context_norm` of every decoder layer normalises the same encoder context (decoder_embeddings.py:141-145):
+    one launch computes all of them from one read of the context (mmfm_layernorm_fwd_multi), and one backward launch
+    normalises the gamma-weighted sum of their upstream gradients (mmfm_layernorm_bwd_multi) instead of n passes over the
+    context with n read-modify-writes of its gradient.  Their gamma / beta gradients then become final after the LAST
+    decoder layer of the backward, so they move behind the decoder layers in the flat gradient order.
+    MMFM_FUSE_CTX_LN=0 keeps the per-layer kernels (ScaleNorm and widths the fused kernels do not take always do)."""
+    if os.environ.get("MMFM_FUSE_CTX_LN", "1") == "0" or n_dec < 2:
+        return False
+    w = named.get("decoder.0.context_norm.weight")
+    if w is None:
+        return False
+    H = w.numel()
+    return H in (128, 256, 512) and (H // 128) * n_dec <= 12
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -124,11 +141,15 @@ class ParamStore:
             for m in reversed(list(dec.keys())):
                 order += lin(f"{prefix}decoder_embeddings.{m}.out")
         order += lin("decoder_norm")
+        fuse_ctx = fuse_context_norms(named, model.n_dec_layers)
         for i in reversed(range(model.n_dec_layers)):
             p = f"decoder.{i}"
             order += lin(f"{p}.mlp.down_proj") + lin(f"{p}.mlp.up_proj") + lin(f"{p}.ln2")
-            order += attn(f"{p}.cross_attn", False) + lin(f"{p}.context_norm") + lin(f"{p}.query_norm")
+            order += attn(f"{p}.cross_attn", False) + ([] if fuse_ctx else lin(f"{p}.context_norm")) + lin(f"{p}.query_norm")
             order += attn(f"{p}.attn", True) + lin(f"{p}.ln1")
+        if fuse_ctx:   # their gradients come out of ONE launch after the last decoder layer of the backward
+            for i in reversed(range(model.n_dec_layers)):
+                order += lin(f"decoder.{i}.context_norm")
         order += lin("decoder_proj_context") + lin("encoder_norm")
         for i in reversed(range(model.n_enc_layers)):
             p = f"encoder.{i}"
@@ -519,6 +540,16 @@ class Plan:
 
         # ---- decoder (decoder_embeddings.py:133-147; mm.py:207-214) ----------------------------------------
         dec_mode = MASK_CAUSAL if eng.causal else MASK_KEY
+        if eng.fuse_ctx:   # every layer's context_norm(context) from one read of the context
+            names = [f"decoder.{i}.context_norm" for i in range(eng.Ld)]
+            for n in names:
+                A[n] = b16(R, H)
+            cmean, crstd = torch.empty(R, device=self.ctx.device), torch.empty(R, device=self.ctx.device)
+            self._keep += [cmean, crstd]
+            for n in names:
+                self.stats[n] = (cmean, crstd)
+            ops.layernorm_fwd_multi(self.ctx, [st.p(n + ".weight") for n in names], [st.p(n + ".bias") for n in names],
+                                    [A[n] for n in names], cmean, crstd, R=R, H=H)
         for i in range(eng.Ld):
             pre = f"decoder.{i}"
             self.ys += [f32(R, H), f32(R, H), f32(R, H)]
@@ -527,9 +558,11 @@ class Plan:
                        eng.sep)
             # cross attention: q from query_norm(y), k/v from context_norm(context), mask = ENCODER mask
             xa = pre + ".cross_attn"
-            A[pre + ".query_norm"], A[pre + ".context_norm"] = b16(R, H), b16(R, H)
+            A[pre + ".query_norm"] = b16(R, H)
             self._ln_fwd(y1, pre + ".query_norm", A[pre + ".query_norm"], self.stats)
-            self._ln_fwd(self.ctx, pre + ".context_norm", A[pre + ".context_norm"], self.stats)
+            if not eng.fuse_ctx:
+                A[pre + ".context_norm"] = b16(R, H)
+                self._ln_fwd(self.ctx, pre + ".context_norm", A[pre + ".context_norm"], self.stats)
             A[xa + ".q"], A[xa + ".kv"] = b16(R, H), b16(R, 2 * H)
             ops.gemm_tn(A[pre + ".query_norm"], sh.nat[xa + ".query"], A[xa + ".q"], bias=self._bias([xa + ".query.bias"]))
             ops.gemm_tn(A[pre + ".context_norm"], sh.nat[xa + ".kv"], A[xa + ".kv"],
@@ -635,6 +668,7 @@ class Plan:
         # ---- decoder layers --------------------------------------------------------------------------------
         dec_mode = MASK_CAUSAL if eng.causal else MASK_KEY
         dqx, dkvx = b16(R, H), b16(R, 2 * H)
+        dctx: List[torch.Tensor] = []
         for i in reversed(range(eng.Ld)):
             pre = f"decoder.{i}"
             y0, y1, y2, y3 = self.ys[3 * i: 3 * i + 4]
@@ -646,15 +680,29 @@ class Plan:
                             SIDE_DEC, False, grads=(d_ao, dqx, dkvx[:, :H], dkvx[:, H:]), prep_done=fused)
             lin_bwd(dqx, A[pre + ".query_norm"], xa + ".query", xa + ".query", dh)
             self._ln_bwd(dh, y1, pre + ".query_norm", G, G, Gb, NO_DROP)
-            lin_bwd(dkvx, A[pre + ".context_norm"], None, xa + ".kv", dh,
-                    wnames=[xa + ".key.weight", xa + ".value.weight"], bnames=[xa + ".key.bias", xa + ".value.bias"])
-            first = i == eng.Ld - 1
-            self._ln_bwd(dh, self.ctx, pre + ".context_norm", None if first else Gctx, Gctx, Gcb if i == 0 else None,
-                         NO_DROP)
+            if eng.fuse_ctx:    # the layer's gradient wrt its normalised context is kept until the last layer is through
+                dctx.append(b16(R, H))
+                lin_bwd(dkvx, A[pre + ".context_norm"], None, xa + ".kv", dctx[-1],
+                        wnames=[xa + ".key.weight", xa + ".value.weight"], bnames=[xa + ".key.bias", xa + ".value.bias"])
+            else:
+                lin_bwd(dkvx, A[pre + ".context_norm"], None, xa + ".kv", dh,
+                        wnames=[xa + ".key.weight", xa + ".value.weight"], bnames=[xa + ".key.bias", xa + ".value.bias"])
+                first = i == eng.Ld - 1
+                self._ln_bwd(dh, self.ctx, pre + ".context_norm", None if first else Gctx, Gctx, Gcb if i == 0 else None,
+                             NO_DROP)
             prev = self._drop(SITE_MLP, i - 1, SIDE_DEC, hp["dec_dropout"]) if i > 0 else NO_DROP
             attn_bwd(pre + ".attn", y0, pre + ".ln1", G, dec_mode, hp["dec_heads"], hp["dec_dropout"], i, SIDE_DEC,
                      eng.sep, Gb if i > 0 else None, prev)
-            mark(f"decoder.{i - 1}.mlp.down_proj.weight" if i > 0 else "decoder_proj_context.weight")
+            if i > 0:
+                mark(f"decoder.{i - 1}.mlp.down_proj.weight")
+            elif eng.fuse_ctx:
+                mark(f"decoder.{eng.Ld - 1}.context_norm.weight")
+        if eng.fuse_ctx:   # gradient of the context through every layer's context_norm: one launch
+            names = [f"decoder.{i}.context_norm" for i in reversed(range(eng.Ld))]      # the order of dctx
+            cmean, crstd = self.stats[names[0]]
+            ops.layernorm_bwd_multi(dctx, self.ctx, cmean, crstd, [st.p(n + ".weight") for n in names], Gctx, Gcb,
+                                    [st.g(n + ".weight") for n in names], [st.g(n + ".bias") for n in names], R=R, H=H)
+        mark("decoder_proj_context.weight")
 
         # ---- context projection + encoder ------------------------------------------------------------------
         lin_bwd(Gcb, A["encoder_norm"], "decoder_proj_context", "decoder_proj_context", dh)
@@ -775,6 +823,7 @@ class Engine:
         loss_kind = adapter.loss_kinds(model)
         self.H = model.hidden_size
         self.Le, self.Ld = model.n_enc_layers, model.n_dec_layers
+        self.fuse_ctx = fuse_context_norms(dict(model.named_parameters(remove_duplicate=False)), self.Ld)
         self.causal, self.sep = bool(model.decoder_causal_mask), bool(model.decoder_sep_mask)
         if hp["enc_act"] != "gelu" or hp["dec_act"] != "gelu":
             raise NotImplementedError("only act='gelu' (mm.yaml:44) is built for the transformer MLP")

@@ -223,6 +223,27 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dxb, drop: DropSpec, dgamm
                                            + (2 if dxb is not None else 0))})
 
 
+def layernorm_fwd_multi(x, gammas, betas, ys, mean, rstd, *, R: int, H: int, eps: float = 1e-5) -> None:
+    """Several LayerNorms over one input (the decoder layers' context_norm): x is read once, len(ys) bf16 outputs."""
+    a = _lib.LnMultiArgs()
+    a.x, a.R, a.H, a.n, a.eps = x.data_ptr(), R, H, len(ys), eps
+    for l, (g, b, y) in enumerate(zip(gammas, betas, ys)):
+        a.gamma[l], a.beta[l], a.y[l] = g.data_ptr(), b.data_ptr(), y.data_ptr()
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    _launch("mmfm_layernorm_fwd_multi", C.byref(a), keep=(a,), meta={"bytes": float(R) * H * (4 + 2 * len(ys))})
+
+
+def layernorm_bwd_multi(dys, x, mean, rstd, gammas, dx, dxb, dgammas, dbetas, *, R: int, H: int) -> None:
+    """dx = LN'(sum_l dy_l . gamma_l) (written, not accumulated) + optional bf16 copy; dgamma_l / dbeta_l accumulate."""
+    a = _lib.LnMultiArgs()
+    a.x, a.R, a.H, a.n, a.eps = x.data_ptr(), R, H, len(dys), 0.0
+    for l, (dy, g, dg, db) in enumerate(zip(dys, gammas, dgammas, dbetas)):
+        a.dy[l], a.gamma[l], a.dgamma[l], a.dbeta[l] = dy.data_ptr(), g.data_ptr(), _p(dg), _p(db)
+    a.mean, a.rstd, a.dx, a.dxb = mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), _p(dxb)
+    _launch("mmfm_layernorm_bwd_multi", C.byref(a), keep=(a,),
+            meta={"bytes": float(R) * H * (4 + 2 * len(dys) + 4 + (2 if dxb is not None else 0))})
+
+
 def scalenorm_fwd(x, g, y, rnorm, *, R: int, H: int, eps: float = 1e-5) -> None:
     _launch("mmfm_scalenorm_fwd", x.data_ptr(), g.data_ptr(), y.data_ptr(), rnorm.data_ptr(), R, H, eps,
             meta={"bytes": 6.0 * R * H})

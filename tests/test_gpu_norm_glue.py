@@ -232,3 +232,35 @@ def test_cast_multi_and_scale():
     assert torch.equal(x, x0)
     ops.scale_inplace(x, torch.tensor([0.5], device="cuda"))
     assert torch.equal(x, x0 * 0.5)
+
+
+@pytest.mark.parametrize("R,H,n", [(1000, 256, 5), (77, 128, 8), (300, 512, 3), (64, 256, 1)])
+def test_layernorm_multi_matches_n_separate_layernorms(R, H, n):
+    """The decoder layers' context_norm share their input (decoder_embeddings.py:141-145): one launch per direction
+    against n torch LayerNorms over the same tensor and the sum of their input gradients."""
+    from multi_modal_foundation_model_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn(R, H, generator=g, device="cuda") * 1.7 + 0.3).requires_grad_(True)
+    gam = [(1.0 + 0.2 * torch.randn(H, generator=g, device="cuda")).requires_grad_(True) for _ in range(n)]
+    bet = [(0.1 * torch.randn(H, generator=g, device="cuda")).requires_grad_(True) for _ in range(n)]
+    ys = [torch.empty(R, H, device="cuda", dtype=torch.bfloat16) for _ in range(n)]
+    mean, rstd = torch.empty(R, device="cuda"), torch.empty(R, device="cuda")
+    ops.layernorm_fwd_multi(x.detach(), [t.detach() for t in gam], [t.detach() for t in bet], ys, mean, rstd, R=R, H=H)
+    refs = [torch.nn.functional.layer_norm(x, (H,), gam[l], bet[l], 1e-5) for l in range(n)]
+    for l in range(n):
+        assert (ys[l].float() - refs[l]).abs().max().item() < 3e-2
+    assert torch.allclose(mean, x.detach().mean(1), atol=1e-5)
+    dys = [(torch.randn(R, H, generator=g, device="cuda") * 0.1).to(torch.bfloat16) for _ in range(n)]
+    sum(( refs[l] * dys[l].float()).sum() for l in range(n)).backward()
+    dx = torch.empty(R, H, device="cuda")
+    dxb = torch.empty(R, H, device="cuda", dtype=torch.bfloat16)
+    dgs = [torch.zeros(H, device="cuda") for _ in range(n)]
+    dbs = [torch.zeros(H, device="cuda") for _ in range(n)]
+    ops.layernorm_bwd_multi(dys, x.detach(), mean, rstd, [t.detach() for t in gam], dx, dxb, dgs, dbs, R=R, H=H)
+    torch.cuda.synchronize()
+    scale = x.grad.abs().max().item()
+    assert (dx - x.grad).abs().max().item() < 2e-3 * scale + 1e-5
+    assert (dxb.float() - x.grad).abs().max().item() < 1e-2 * scale + 1e-4
+    for l in range(n):
+        assert (dgs[l] - gam[l].grad).abs().max().item() < 2e-3 * gam[l].grad.abs().max().item() + 1e-4
+        assert (dbs[l] - bet[l].grad).abs().max().item() < 2e-3 * bet[l].grad.abs().max().item() + 1e-4
