@@ -498,6 +498,8 @@ int launch_attn_bwd_ws(const mmfm_attn_args* a, const AttnParams& p, cudaStream_
   const int n_items = a->B * a->n_heads;
   int grid = device_sm_count();
   if (grid > n_items) grid = n_items;
+  // dq / dk / dv are column blocks of one [B Sq, 3 H] gradient buffer in the model: the QKV dgrad GEMM reads it next
+  set_l2_window(a->dq, (size_t)a->B * a->Sq * (size_t)a->lddq * 2);
   if (drop) MMFM_CHECK_CUDA(launch_pdl(attn_bwd_ws_kernel<true>, dim3(grid), dim3(kWsThreads), kWsSmem, st, tq, tdo, tk, tv, tdq, tdk, tdv, p, npk, n_items));
   else MMFM_CHECK_CUDA(launch_pdl(attn_bwd_ws_kernel<false>, dim3(grid), dim3(kWsThreads), kWsSmem, st, tq, tdo, tk, tv, tdq, tdk, tdv, p, npk, n_items));
   return 0;

@@ -560,6 +560,8 @@ static int launch_fwd_pipe_d(const mmfm_attn_args* a, const AttnParams& p, cudaS
   const int n_items = (int)n_items_ll;
   int grid = device_sm_count();
   if (grid > n_items) grid = n_items;
+  const size_t o_bytes = (size_t)a->B * a->Sq * (size_t)a->ldo * 2;
+  set_l2_window(a->o, o_bytes);   // read next by the out-projection GEMM
   if (drop) MMFM_CHECK_CUDA(launch_pdl(attn_fwd_pipe_kernel<D, true>, dim3(grid), dim3(kPipeThreads), Cfg::kSmem, st, tq, tk, tv, p, bn, nb, n_qp, n_items));
   else MMFM_CHECK_CUDA(launch_pdl(attn_fwd_pipe_kernel<D, false>, dim3(grid), dim3(kPipeThreads), Cfg::kSmem, st, tq, tk, tv, p, bn, nb, n_qp, n_items));
   return 0;

@@ -792,6 +792,7 @@ static int launch_tn(const mmfm_gemm_args* a, cudaStream_t st) {
     grid = per_n * tiles_n;
     bstat = 1;
   }
+  set_l2_window(a->D, (size_t)a->M * (size_t)a->ldd * (a->d_fp32 ? 4 : 2));   // the output is the next kernel's input
   MMFM_CHECK_CUDA(launch_pdl(gemm_tn_kernel<BN, STAGES, EPI>, dim3(grid), dim3(kTnThreads), smem, st, tmA, tmB, *a, tiles_n,
                              n_tiles, bstat));
   return 0;

@@ -475,6 +475,7 @@ static int launch_ts_bn(const mmfm_gemm_args* a, cudaStream_t st) {
     grid = (sms / tiles_n) * tiles_n;
     smem = 1024 + b_res + (size_t)nst * a_stage + 2 * (size_t)Cfg::kBuf;
   }
+  set_l2_window(a->D, (size_t)a->M * (size_t)a->ldd * (a->d_fp32 ? 4 : 2));   // the output is the next kernel's input
   MMFM_CHECK_CUDA(launch_pdl(gemm_tn_ts_kernel<EPI, BN>, dim3(grid), dim3(kTsThreads), smem, st, tmA, tmB, tmD, tmD2, tmIn, *a,
                              tiles_n, n_tiles, bstat, nst));
   return 0;

@@ -105,6 +105,53 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+static thread_local const void* g_win_ptr = nullptr;
+static thread_local size_t g_win_bytes = 0;
+
+static int l2_persist_state() {   // -1 off, else the maximum window size in MB
+  static int state = -2;
+  if (state == -2) {
+    const char* e = getenv("MMFM_L2_PERSIST");
+    state = -1;
+    if (e && e[0] == '1') {
+      int dev = 0, max_persist = 0, max_win = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+      const char* mb = getenv("MMFM_L2_PERSIST_MB");       // set-aside = largest window taken (default: the device maximum)
+      if (mb && atoi(mb) > 0 && ((size_t)atoi(mb) << 20) < (size_t)max_persist) max_persist = atoi(mb) << 20;
+      if (max_persist > 0 && max_win > 0 &&
+          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist) == cudaSuccess) {
+        state = max_persist >> 20;
+        if (getenv("MMFM_L2_PERSIST_VERBOSE"))
+          fprintf(stderr, "mmfm: persisting L2 set-aside %d MB, window limit %d MB\n", max_persist >> 20, max_win >> 20);
+      }
+    }
+  }
+  return state;
+}
+
+void set_l2_window(const void* ptr, size_t bytes) {
+  g_win_ptr = ptr;
+  g_win_bytes = bytes;
+}
+
+bool take_l2_window(cudaAccessPolicyWindow* w) {
+  const void* ptr = g_win_ptr;
+  const size_t bytes = g_win_bytes;
+  g_win_ptr = nullptr;
+  g_win_bytes = 0;
+  const int lim = l2_persist_state();
+  if (lim < 0 || ptr == nullptr || bytes == 0) return false;
+  if (bytes > ((size_t)lim << 20)) return false;   // an output larger than the set-aside would only thrash it
+  w->base_ptr = const_cast<void*>(ptr);
+  w->num_bytes = bytes;
+  w->hitRatio = 1.0f;
+  w->hitProp = cudaAccessPropertyPersisting;
+  w->missProp = cudaAccessPropertyStreaming;
+  return true;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {

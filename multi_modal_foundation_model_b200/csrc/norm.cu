@@ -535,6 +535,7 @@ extern "C" int mmfm_layernorm_fwd(const float* x, const float* gamma, const floa
                "mmfm_layernorm_fwd: modality-major remap needs S %% T == 0 and R %% S == 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ln_grid_fwd(R, H);
+  set_l2_window(y, (size_t)R * H * 2);   // read next by the projection GEMM
 #define LN_FWD(NV) \
   MMFM_CHECK_CUDA(launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(kLnWarps * 32), 0, st, x, gamma, beta, (bf16*)y, mean, rstd, R, H, eps, modmajor_T, S))
   switch (H) {
@@ -567,6 +568,7 @@ extern "C" int mmfm_layernorm_bwd(const void* dy, const float* x, const float* m
   cudaStream_t st = (cudaStream_t)stream;
   // fewer, fatter CTAs than the forward (every CTA ends with 2*H atomics); exactly one resident wave
   const int want = (R + kLnWarps * 4 - 1) / (kLnWarps * 4);
+  if (dxb) set_l2_window(dxb, (size_t)R * H * 2);   // read next by a dgrad GEMM
 #define LN_BWD(NV)                                                                                                \
   do {                                                                                                            \
     static int cap = 0;                                                                                           \
