@@ -436,6 +436,35 @@ MMFM_DEVINL uint64_t fadd2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// gelu and its derivative for a PAIR of arguments with packed fp32 arithmetic (FMUL2 / FFMA2): the same Abramowitz-Stegun
+// evaluation as gelu_erf_both, half the issue slots for everything but the two MUFU ops per element.  The MLP-up epilogue
+// of the TMA-store GEMM evaluates 26 M of these per launch and is bound by issue slots.
+MMFM_DEVINL void gelu_erf_both2(float x0, float x1, float& g0, float& g1, float& d0, float& d1) {
+  const uint64_t x = pack_f2(x0, x1);
+  const uint64_t z = fmul2(x, pack_f2(0.70710678118654752f, 0.70710678118654752f));
+  float z0, z1;
+  unpack_f2(z, z0, z1);
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.3275911f, fabsf(z0), 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.3275911f, fabsf(z1), 1.0f)));
+  float a0, a1;
+  unpack_f2(fmul2(fmul2(z, z), pack_f2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t t = pack_f2(t0, t1), e = pack_f2(e0, e1);
+  uint64_t q = ffma2(pack_f2(1.061405429f, 1.061405429f), t, pack_f2(-1.453152027f, -1.453152027f));
+  q = ffma2(q, t, pack_f2(1.421413741f, 1.421413741f));
+  q = ffma2(q, t, pack_f2(-0.284496736f, -0.284496736f));
+  q = ffma2(q, t, pack_f2(0.254829592f, 0.254829592f));
+  q = fmul2(q, t);
+  float r0, r1;
+  unpack_f2(ffma2(q, fmul2(e, pack_f2(-1.0f, -1.0f)), pack_f2(1.0f, 1.0f)), r0, r1);   // 1 - poly * exp(-z^2) = erf(|z|)
+  const uint64_t erf2 = pack_f2(copysignf(r0, z0), copysignf(r1, z1));
+  const uint64_t cdf = ffma2(erf2, pack_f2(0.5f, 0.5f), pack_f2(0.5f, 0.5f));
+  unpack_f2(fmul2(x, cdf), g0, g1);
+  unpack_f2(ffma2(fmul2(x, pack_f2(0.3989422804014327f, 0.3989422804014327f)), e, cdf), d0, d1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // warp-level mma.sync path (attention core: d_head 32/64 tiles are softmax-bound)
 // ------------------------------------------------------------------------------------------------

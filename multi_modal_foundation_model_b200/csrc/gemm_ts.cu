@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gemm_tn_ts_kernel(const __grid_
             float d2[16];
             if (EPI == TS_GELU_DG) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) gelu_erf_both(v[j], v[j], d2[j]);
+              for (int j = 0; j < 16; j += 2) gelu_erf_both2(v[j], v[j + 1], v[j], v[j + 1], d2[j], d2[j + 1]);
             }
             uint4 wdrop = make_uint4(0u, 0u, 0u, 0u);
             if (EPI == TS_ROWDOT && drop)
