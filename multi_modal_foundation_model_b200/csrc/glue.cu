@@ -419,7 +419,24 @@ __global__ void __launch_bounds__(256) smallc_embed_bwd16_kernel(
   for (int k = 0; k < 16; ++k) {
     ab2[k] = 0.f;
 #pragma unroll
-    for (int j = 0; j < C2; ++j) { w2[k][j] = W2[(16 * g + k) * C2 + j]; aw2[k][j] = 0.f; }
+    for (int j = 0; j < C2; ++j) aw2[k][j] = 0.f;
+  }
+  {   // this thread's slice of W2 (16 rows x C2) is contiguous: vector loads instead of 16 * C2 scalar ones
+    const float* wsrc = W2 + (size_t)16 * g * C2;
+    if constexpr (C2 % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < 16 * C2 / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wsrc) + q);
+        w2[(4 * q) / C2][(4 * q) % C2] = t.x; w2[(4 * q + 1) / C2][(4 * q + 1) % C2] = t.y;
+        w2[(4 * q + 2) / C2][(4 * q + 2) % C2] = t.z; w2[(4 * q + 3) / C2][(4 * q + 3) % C2] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16 * C2 / 2; ++q) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(wsrc) + q);
+        w2[(2 * q) / C2][(2 * q) % C2] = t.x; w2[(2 * q + 1) / C2][(2 * q + 1) % C2] = t.y;
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < C2; ++j) {
@@ -431,12 +448,13 @@ __global__ void __launch_bounds__(256) smallc_embed_bwd16_kernel(
   for (long long wb = slot0 - lane; wb < slots; wb += stride) {
     const long long slot = wb + lane;
     const bool valid = slot < slots;
-    const long long r = valid ? slot / gpr : 0;
-    const long long b = r / T;
-    const int t = (int)(r - b * T);
+    const int gshift = 31 - __clz(gpr);                       // gpr is a power of two
+    const long long r = valid ? (slot >> gshift) : 0;
+    const int b = (int)r / T;                                  // B * T < 2^31
+    const int t = (int)r - b * T;
     float d[16];
     const bool zero = !valid || (row_zero && row_zero[off + t]);
-    const long long orow = (b * S + off + t) * H + 16 * g;
+    const long long orow = ((long long)b * S + off + t) * H + 16 * g;
 #pragma unroll
     for (int k4 = 0; k4 < 16; k4 += 4) {
       const float4 v = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(dx + orow + k4));
@@ -447,9 +465,11 @@ __global__ void __launch_bounds__(256) smallc_embed_bwd16_kernel(
 #pragma unroll
       for (int k = 0; k < 16; ++k) d[k] = drop_byte(w, k) < drop.thresh ? 0.f : d[k] * drop.scale;
     }
-    float hj[C2], dh[C2];
+    float hj[C2], dh[C2], xin[C];
 #pragma unroll
     for (int j = 0; j < C2; ++j) { hj[j] = __ldg(hid + r * C2 + j); dh[j] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < C; ++c) xin[c] = __ldg(in + r * C + c);   // (in flight with the rest: its consumer waited 16 % of the kernel)
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       ab2[k] += d[k];
@@ -475,7 +495,7 @@ __global__ void __launch_bounds__(256) smallc_embed_bwd16_kernel(
         }
         ab1[j] += v;
 #pragma unroll
-        for (int c = 0; c < C; ++c) aw1[j][c] = fmaf(v, __ldg(in + r * C + c), aw1[j][c]);
+        for (int c = 0; c < C; ++c) aw1[j][c] = fmaf(v, xin[c], aw1[j][c]);
       }
     }
   }
