@@ -291,10 +291,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) attn_fwd_pipe_kernel(const __
               ++cnt[X];
               tc_fence_after();
               const uint32_t t_s = tmem_base + (uint32_t)(X * Cfg::kSW), t_o = tmem_base + (uint32_t)(2 * Cfg::kSW + X * D);
-              for (int kk = 0; kk < nks; ++kk)
-                umma_bf16_ts(t_o, t_s + 32u * (kk >> 1) + 8u * (kk & 1),
-                             make_smem_desc(av + (uint32_t)kk * 16u * kRowBytes, kSbo, kSbo, kLayout), idesc_pv,
-                             (j > 0 || kk > 0) ? 1u : 0u);
+              // 16-key steps in pairs with incremental operands: the issue loop is a dependent chain of address arithmetic in
+              // ONE thread, and the tile's epilogue waits for the last of these products
+              uint64_t dv = make_smem_desc(av, kSbo, kSbo, kLayout);
+              const uint64_t dstep = (uint64_t)((16u * kRowBytes) >> 4);
+              uint32_t ta = t_s;
+              uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll 1
+              for (int kk = 0; kk + 1 < nks; kk += 2) {
+                umma_bf16_ts(t_o, ta, dv, idesc_pv, acc);
+                umma_bf16_ts(t_o, ta + 8u, dv + dstep, idesc_pv, 1u);
+                acc = 1u;
+                ta += 32u;
+                dv += 2 * dstep;
+              }
+              if (nks & 1) umma_bf16_ts(t_o, ta, dv, idesc_pv, acc);
               umma_commit(&pv_done[X]);
             }
             if (X == lastX) {      // every MMA that reads this K/V stage (and, on the last block, the Q stage) is issued
