@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
       mbar_init(&ld_bar[i], 1);
       mbar_init(&s_bar[i], 1);
       mbar_init(&dp_bar[i], 1);
-      mbar_init(&pa_bar[i], kWsMathWarps);
-      mbar_init(&ds_bar[i], kWsMathWarps);
+      mbar_init(&pa_bar[i], kWsMathWarps * 32);
+      mbar_init(&ds_bar[i], kWsMathWarps * 32);
     }
     mbar_init(&done_bar, 1);
     mbar_init(&staged_bar, kWsMathWarps);
@@ -409,8 +409,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           DBG_WS(6 + 16 * qt + 4 * kh);
           fence_proxy_async();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&pa_bar[kh]);
+          mbar_arrive(&pa_bar[kh]);
         }
 
         // the previous item's accumulators: its products completed long ago; dQ / dK are first overwritten by the
@@ -458,8 +457,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) attn_bwd_ws_kernel(
           DBG_WS(14 + 16 * qt + 4 * kh);
           fence_proxy_async();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&ds_bar[kh]);
+          mbar_arrive(&ds_bar[kh]);
         }
       }
     }
