@@ -208,3 +208,27 @@ def test_heldout_mask_compact_form_equals_reference():
         dense = r["dense_eval_mask"]().numpy()
         assert np.array_equal(dense, z[f"case{i}/eval_mask"]), (mode, i)
         assert r["eval_mask"].dtype == torch.int64 and np.array_equal(r["eval_mask"].numpy(), dense[:, :, 0]), (mode, i)
+
+
+def test_flat_gradient_order_with_fused_context_norms(monkeypatch):
+    """The decoder layers' context_norm gradients come out of ONE launch after the last decoder layer of the backward
+    (engine.fuse_context_norms), so in the flat gradient order -- reverse execution order, the data-parallel bucket
+    order -- they sit behind every decoder-layer parameter and in front of decoder_proj_context; with the fusion off they
+    stay inside their layers.  Either way the order is a permutation of all parameters."""
+    from multi_modal_foundation_model_b200 import engine
+    from multi_modal_foundation_model_b200.model import build_model
+    m = build_model(40, 2, default_model_config(n_layers=3))
+    named = dict(m.named_parameters(remove_duplicate=False))
+    for fused in (True, False):
+        monkeypatch.setenv("MMFM_FUSE_CTX_LN", "1" if fused else "0")
+        assert engine.fuse_context_norms(named, 3) is fused
+        order = engine.ParamStore._execution_reverse_order(m, named)
+        assert sorted(order) == sorted(named)
+        ctx = [order.index(f"decoder.{i}.context_norm.weight") for i in range(3)]
+        last_layer_param = max(order.index(n) for n in order if n.startswith("decoder.") and ".context_norm." not in n)
+        if fused:
+            assert min(ctx) > last_layer_param and max(ctx) < order.index("decoder_proj_context.weight")
+            assert ctx == sorted(ctx, reverse=True)          # layer 2 first: the order of the backward's dY list
+        else:
+            assert min(ctx) < last_layer_param
+    assert not engine.fuse_context_norms(named, 1)           # a single decoder layer has nothing to share
