@@ -19,13 +19,16 @@
 //
 // Measured on B200 (tools/attn_bench.py, default shape, dropout on, preparation kernel included): 201 us for the block-
 // synchronous kernel -> 141 us (this structure) -> 135 us with the issuer's MMA batches unrolled (a rolled loop spends
-// ~100 clocks of descriptor arithmetic per 41-clock MMA: tools/micro/umma_rate.cu).  What a globaltimer trace of this
+// ~100 clocks of descriptor arithmetic per 41-clock MMA: tools/micro/umma_rate.cu) -> 132 us with every math thread
+// arriving on the hand-over barriers itself (a warp-level sync + one elected arrival added latency).  What a globaltimer trace of this
 // kernel (tools/micro/bwd_ws_timing.py) shows per item: probability passes at the MUFU bound (0.54 us per 128 x 128
 // block = 16 exp2 per clock and SM), dS passes ~0.42 us, and about as much again in hand-over latency between passes.
 // Variants that were built, verified and measured SLOWER, so they are not here: eight math warps with 168 registers
 // (147 us: one or two warps per scheduler cannot cover the MUFU / tcgen05.ld latencies); two column groups that own one
 // key half each and run one pass out of phase, with 8 or 16 math warps (157 - 187 us: same reason); 8-key work units dealt
-// evenly to the column groups (the predicated unit bodies cost more instructions than the balance wins); setmaxnreg
+// evenly to the column groups (the predicated unit bodies cost more instructions than the balance wins); a polynomial
+// exp2 on the FMA pipe for a third of the pairs (142 us: packed FFMA2 saves issue slots, not pipe cycles); the product
+// -p * delta moved into the probability pass (136 us); setmaxnreg
 // (the register pool only holds what a warpgroup released: the math warps cannot get past 112, and a 32-register issuer
 // spills inside its MMA batches).
 #include "attn_common.cuh"
