@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_multi_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = a.R, H = a.H;
   const float invH = 1.0f / (float)H;
+  constexpr int U = (NV * NL <= 10) ? 2 : 1;   // rows per warp in flight (their loads are issued before the first reduction)
   float4 accg[NL][NV], accb[NL][NV];
 #pragma unroll
   for (int l = 0; l < NL; ++l)
@@ -326,53 +327,67 @@ __global__ void __launch_bounds__(kLnWarps * 32) layernorm_bwd_multi_kernel(cons
       accg[l][j] = make_float4(0.f, 0.f, 0.f, 0.f);
       accb[l][j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  for (long long r = (long long)blockIdx.x * kLnWarps + warp; r < R; r += (long long)gridDim.x * kLnWarps) {
-    const float mu = __ldg(a.mean + r), rs = __ldg(a.rstd + r);
-    uint2 dv[NL][NV];
+  for (long long r0 = ((long long)blockIdx.x * kLnWarps + warp) * U; r0 < R; r0 += (long long)gridDim.x * kLnWarps * U) {
+    uint2 dv[U][NL][NV];
+    float4 xv[U][NV];
+    float mu[U], rs[U];
 #pragma unroll
-    for (int l = 0; l < NL; ++l)      // every layer's gradient row in flight together with x
+    for (int u = 0; u < U; ++u) {
+      const long long r = (r0 + u < R) ? r0 + u : r0;   // (a row past the end re-reads row r0 and is not written)
+      mu[u] = __ldg(a.mean + r);
+      rs[u] = __ldg(a.rstd + r);
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        dv[l][j] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(a.dy[l]) + r * H) + lane + 32 * j);
-    float4 xh[NV], gd[NV];
+      for (int l = 0; l < NL; ++l)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + r * H) + lane + 32 * j);
-      xh[j] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      gd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NV; ++j)
+          dv[u][l][j] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(a.dy[l]) + r * H) + lane + 32 * j);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) xv[u][j] = __ldg(reinterpret_cast<const float4*>(a.x + r * H) + lane + 32 * j);
     }
 #pragma unroll
-    for (int l = 0; l < NL; ++l)
+    for (int u = 0; u < U; ++u) {
+      if (r0 + u >= R) break;
+      const long long r = r0 + u;
+      float4 xh[NV], gd[NV];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[l]) + lane + 32 * j);
-        const float2 d01 = unpack_bf16x2(dv[l][j].x), d23 = unpack_bf16x2(dv[l][j].y);
-        accb[l][j].x += d01.x; accb[l][j].y += d01.y; accb[l][j].z += d23.x; accb[l][j].w += d23.y;
-        accg[l][j].x = fmaf(d01.x, xh[j].x, accg[l][j].x); accg[l][j].y = fmaf(d01.y, xh[j].y, accg[l][j].y);
-        accg[l][j].z = fmaf(d23.x, xh[j].z, accg[l][j].z); accg[l][j].w = fmaf(d23.y, xh[j].w, accg[l][j].w);
-        gd[j].x = fmaf(d01.x, gm.x, gd[j].x); gd[j].y = fmaf(d01.y, gm.y, gd[j].y);
-        gd[j].z = fmaf(d23.x, gm.z, gd[j].z); gd[j].w = fmaf(d23.y, gm.w, gd[j].w);
+        xh[j] = make_float4((xv[u][j].x - mu[u]) * rs[u], (xv[u][j].y - mu[u]) * rs[u], (xv[u][j].z - mu[u]) * rs[u],
+                            (xv[u][j].w - mu[u]) * rs[u]);
+        gd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      s1 += (gd[j].x + gd[j].y) + (gd[j].z + gd[j].w);
-      s2 += (gd[j].x * xh[j].x + gd[j].y * xh[j].y) + (gd[j].z * xh[j].z + gd[j].w * xh[j].w);
-    }
-    const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+      for (int l = 0; l < NL; ++l)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      float4 o;
-      o.x = rs * (gd[j].x - m1 - xh[j].x * m2);
-      o.y = rs * (gd[j].y - m1 - xh[j].y * m2);
-      o.z = rs * (gd[j].z - m1 - xh[j].z * m2);
-      o.w = rs * (gd[j].w - m1 - xh[j].w * m2);
-      reinterpret_cast<float4*>(a.dx + r * H)[lane + 32 * j] = o;
-      if (a.dxb) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o.x, o.y);
-        pk.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.dxb) + r * H)[lane + 32 * j] = pk;
+        for (int j = 0; j < NV; ++j) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma[l]) + lane + 32 * j);
+          const float2 d01 = unpack_bf16x2(dv[u][l][j].x), d23 = unpack_bf16x2(dv[u][l][j].y);
+          accb[l][j].x += d01.x; accb[l][j].y += d01.y; accb[l][j].z += d23.x; accb[l][j].w += d23.y;
+          accg[l][j].x = fmaf(d01.x, xh[j].x, accg[l][j].x); accg[l][j].y = fmaf(d01.y, xh[j].y, accg[l][j].y);
+          accg[l][j].z = fmaf(d23.x, xh[j].z, accg[l][j].z); accg[l][j].w = fmaf(d23.y, xh[j].w, accg[l][j].w);
+          gd[j].x = fmaf(d01.x, gm.x, gd[j].x); gd[j].y = fmaf(d01.y, gm.y, gd[j].y);
+          gd[j].z = fmaf(d23.x, gm.z, gd[j].z); gd[j].w = fmaf(d23.y, gm.w, gd[j].w);
+        }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        s1 += (gd[j].x + gd[j].y) + (gd[j].z + gd[j].w);
+        s2 += (gd[j].x * xh[j].x + gd[j].y * xh[j].y) + (gd[j].z * xh[j].z + gd[j].w * xh[j].w);
+      }
+      const float m1 = warp_sum(s1) * invH, m2 = warp_sum(s2) * invH;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 o;
+        o.x = rs[u] * (gd[j].x - m1 - xh[j].x * m2);
+        o.y = rs[u] * (gd[j].y - m1 - xh[j].y * m2);
+        o.z = rs[u] * (gd[j].z - m1 - xh[j].z * m2);
+        o.w = rs[u] * (gd[j].w - m1 - xh[j].w * m2);
+        reinterpret_cast<float4*>(a.dx + r * H)[lane + 32 * j] = o;
+        if (a.dxb) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.dxb) + r * H)[lane + 32 * j] = pk;
+        }
       }
     }
   }
