@@ -114,6 +114,9 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __rest
 // position row are summed in registers before one red.global per column; the modality-embedding sums of the lanes are
 // combined in shared memory (one atomic per column per CTA).
 constexpr int kAsmLanes = 4;
+constexpr int kModReplicas = 16;
+__device__ float g_dmod_scratch[kModReplicas][1024];   // H <= 1024 (checked by the launcher); all zero between launches
+__device__ unsigned int g_dmod_ticket;
 __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const float* __restrict__ g2,
                                           const long long* __restrict__ ts, float* __restrict__ dpos,
                                           float* __restrict__ dmod, int B, int T, int S, int off, int H, int bchunk) {
@@ -170,6 +173,11 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const flo
     sm_acc[sl * ncol + c] = accm;
   }
   __syncthreads();
+  // Modality-embedding gradient = sum over ALL rows: hundreds of CTAs adding to the same H addresses serialise in L2
+  // (600 atomics per address at B = 256), so the CTAs spread their sums over kModReplicas scratch copies and the last
+  // CTA to finish (ticket) folds the copies into dmod and clears them for the next launch.  (One launch in flight per
+  // device at a time: the engine issues them on its single stream.)
+  __shared__ bool s_last;
   if (sl == 0) {
     float4 tot = sm_acc[c];
 #pragma unroll
@@ -177,8 +185,22 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, const flo
       const float4 o = sm_acc[l * ncol + c];
       tot.x += o.x; tot.y += o.y; tot.z += o.z; tot.w += o.w;
     }
-    float* dm = dmod + c * 4;
+    float* dm = g_dmod_scratch[(blockIdx.x + blockIdx.y * gridDim.x) % kModReplicas] + c * 4;
     atomicAdd(dm, tot.x); atomicAdd(dm + 1, tot.y); atomicAdd(dm + 2, tot.z); atomicAdd(dm + 3, tot.w);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_dmod_ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int col = threadIdx.x; col < H; col += blockDim.x) {
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < kModReplicas; ++r) sum += atomicExch(&g_dmod_scratch[r][col], 0.f);
+      atomicAdd(dmod + col, sum);
+    }
+    if (threadIdx.x == 0) g_dmod_ticket = 0u;
   }
 }
 
